@@ -1,0 +1,107 @@
+/*
+ * b200vit.h -- C ABI of libb200vit.so: hand-written sm_100a kernels for the ViT encoder forward path.
+ *
+ * The reference (lucidrains/vit-pytorch, /root/reference) is pure Python and has NO plugin / FFI interface;
+ * its operator boundary for this path is the nn.Module surface.  Each entry point below therefore
+ * names the reference *operator sequence* it replaces (file:line), and INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - the caller owns every buffer (including workspaces); the library allocates nothing on the device.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation.
+ *   - return value 0 = success, negative = error; message via b200vit_last_error() (thread local).
+ *   - bf16 = __nv_bfloat16 storage; accumulation, LayerNorm statistics, softmax and the residual stream are fp32.
+ */
+#ifndef B200VIT_H_
+#define B200VIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VIT_OK 0
+#define B200VIT_ERR_INVALID -1  /* bad argument (shape, alignment, null pointer) */
+#define B200VIT_ERR_CUDA -2     /* a CUDA runtime / driver call failed */
+#define B200VIT_ERR_DEVICE -3   /* not an sm_100 device */
+
+/* GEMM epilogue flags (b200vit_gemm_bf16) */
+#define B200VIT_EPI_BIAS 1      /* + bias[n] (fp32) */
+#define B200VIT_EPI_GELU 2      /* exact-erf GELU (nn.GELU default, vit.py:21) */
+#define B200VIT_EPI_RESIDUAL 4  /* + resid[m, n] (fp32); resid may alias out_f32 (in-place residual stream) */
+#define B200VIT_EPI_LNFOLD 8    /* A is the un-normalised bf16 row, W carries gamma: y = rstd_m*(acc - mu_m*s_n) + bias_n */
+#define B200VIT_EPI_STATS 16    /* atomically accumulate per-row (sum, sum^2) of the bf16-rounded result into stats_out */
+
+const char* b200vit_last_error(void);
+int b200vit_version(void);
+/* number of kernels this library has launched in the calling process (all threads) since load / last reset */
+int64_t b200vit_launch_count(void);
+void b200vit_reset_launch_count(void);
+/* 0 when device `dev` is sm_100 and the driver entry points the library needs resolve; negative otherwise */
+int b200vit_device_ok(int dev);
+
+/*
+ * out[M, N] = epilogue( A[M, K] (bf16, row stride lda) x W[N, K]^T (bf16, row stride ldw) ), fp32 accumulate in TMEM.
+ * TMA-fed tcgen05 GEMM, persistent, warp specialised.  Replaces every nn.Linear on the path:
+ *   vit.py:20,23 (FeedForward), vit.py:44,47 (to_qkv / to_out), vit.py:102 (patch projection), vit.py:116 (mlp_head);
+ *   simple_vit.py:30,32,47,48,93,108.
+ * out_bf16 and/or out_f32 (either may be NULL, not both), row stride ldo (elements).
+ * EPI_LNFOLD: ln_sums[M][2] = per-row (sum, sum of squares) of A, ln_dim = K, col_s[N] = sum_k W[n,k] (fp32).
+ * Requirements: A, W 16-byte aligned, lda, ldw multiples of 8, K multiple of 8.
+ */
+int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32,
+                      int64_t ldo, const float* bias, const float* resid, const float* ln_sums, float ln_eps,
+                      const float* col_s, float* stats_out, int M, int N, int K, int flags, void* stream);
+
+/*
+ * LayerNorm over the last dim of an fp32 [M, D] matrix (row stride ldx) -> bf16 and/or fp32 outputs.
+ * Replaces nn.LayerNorm(dim) at vit.py:19,39,69,103 / simple_vit.py:29,42,67,94 (eps 1e-5, biased variance).
+ * gamma/beta fp32 [D] (beta may be NULL: NaViT's bias-free LayerNorm, na_vit.py:82-89).
+ * If row_index != NULL, output row i is computed from input row row_index[i]  (cls pooling: vit.py:135).
+ */
+int b200vit_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                      float* out_f32, int64_t ldo, const int32_t* row_index, int M, int D, float eps, void* stream);
+
+/*
+ * Patchify + LayerNorm(patch_dim): img[B, C, H, W] (bf16, NCHW contiguous) -> A[B*gh*gw, ldo] bf16 with
+ *   A[b*(gh*gw) + h*gw + w, (p1*pw + p2)*C + c] = LN_over_patch(img[b, c, h*ph + p1, w*pw + p2]) * gamma + beta.
+ * Replaces Rearrange('b c (h p1) (w p2) -> b (h w) (p1 p2 c)') + nn.LayerNorm(patch_dim), vit.py:100-101 /
+ * simple_vit.py:91-92.  Columns [patch_dim, ldo) are zero filled (K padding for the GEMM).
+ */
+int b200vit_patchify_ln(const void* img, const float* gamma, const float* beta, void* out_bf16, int64_t ldo, int B,
+                        int C, int H, int W, int ph, int pw, float eps, void* stream);
+
+/*
+ * Token assembly after the patch projection: y[B*n, D] (fp32, patch GEMM output incl. bias) ->
+ *   x[b, t, :] = LN_D(y[b, t - ncls, :]) * gamma + beta + pos[t, :]   for t >= ncls
+ *   x[b, 0, :] = cls[:] + pos[0, :]                                    if ncls == 1
+ * written as the fp32 residual stream x[B*(n+ncls), D].
+ * Replaces nn.LayerNorm(dim) vit.py:103, cls concat vit.py:122-123, pos add vit.py:125-127 (simple_vit.py:94,114).
+ */
+int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls, const float* pos,
+                         float* x, int B, int n, int ncls, int D, float eps, void* stream);
+
+/*
+ * Multi-head softmax attention straight out of the packed QKV buffer:
+ *   qkv[B*N, 3*H*dh] bf16 (columns: [q | k | v], each head-major h*dh + d; vit.py:54-55)
+ *   out[B*N, H*dh]   bf16 (merged heads, vit.py:63) = softmax(q k^T * scale) v          (vit.py:57-62)
+ * One pass over the keys (N <= 256): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ */
+int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
+
+/* Mean over tokens: x[B, N, D] fp32 -> out[B, D] fp32 (vit.py:135 pool == 'mean', simple_vit.py:117). */
+int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream);
+
+/* fp32 -> bf16 cast of a contiguous buffer of n elements (n multiple of 8). */
+int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
+
+/* Experiment knobs for kernel bring-up (not part of the drop-in surface).
+ * key 1: attention P staging (0 = TMEM, 1 = shared memory); key 2/3: V descriptor LBO / SBO bytes. */
+int b200vit_debug_set(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VIT_H_ */

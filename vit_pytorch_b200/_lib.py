@@ -1,0 +1,203 @@
+"""ctypes binding of libb200vit.so (the C ABI declared in include/b200vit.h).
+
+No torch C++ headers are involved: tensors cross the boundary as raw device pointers + sizes, the stream as the
+cudaStream_t handle of torch's current stream.  There is NO fallback here: if the library is missing or a call
+fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libb200vit.so"
+
+EPI_BIAS = 1
+EPI_GELU = 2
+EPI_RESIDUAL = 4
+EPI_LNFOLD = 8
+EPI_STATS = 16
+
+# every symbol include/b200vit.h declares (tests check that the library exports each of them)
+SYMBOLS = [
+    "b200vit_last_error", "b200vit_version", "b200vit_launch_count", "b200vit_reset_launch_count",
+    "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
+    "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+class B200VitError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200VitError(
+            f"{LIB_PATH} not found: build it with `python -m vit_pytorch_b200.build` "
+            "(there is no fallback for the fused CUDA path)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    L.b200vit_last_error.restype = C.c_char_p
+    L.b200vit_last_error.argtypes = []
+    L.b200vit_version.restype = i32
+    L.b200vit_launch_count.restype = i64
+    L.b200vit_reset_launch_count.restype = None
+    L.b200vit_device_ok.restype = i32
+    L.b200vit_device_ok.argtypes = [i32]
+    L.b200vit_gemm_bf16.restype = i32
+    L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp]
+    L.b200vit_layernorm.restype = i32
+    L.b200vit_layernorm.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, f32, vp]
+    L.b200vit_patchify_ln.restype = i32
+    L.b200vit_patchify_ln.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, vp]
+    L.b200vit_embed_tokens.restype = i32
+    L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_attention.restype = i32
+    L.b200vit_attention.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_mean_pool.restype = i32
+    L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.b200vit_cast_f32_bf16.restype = i32
+    L.b200vit_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b200vit_last_error()
+        raise B200VitError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().b200vit_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().b200vit_reset_launch_count()
+
+
+def device_ok(dev: int) -> bool:
+    return lib().b200vit_device_ok(int(dev)) == 0
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str) -> None:
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype:
+        raise B200VitError(f"{name}: expected CUDA {dtype}, got {t.device} {t.dtype}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None,
+         out_f32: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         resid: Optional[torch.Tensor] = None, gelu: bool = False, ln_sums: Optional[torch.Tensor] = None,
+         ln_eps: float = 1e-5, col_s: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
+         n: Optional[int] = None, k: Optional[int] = None) -> None:
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last stride 1)."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
+    _chk(out_bf16, torch.bfloat16, "out_bf16"); _chk(out_f32, torch.float32, "out_f32")
+    for nm, t in (("bias", bias), ("resid", resid), ("ln_sums", ln_sums), ("col_s", col_s), ("stats_out", stats_out)):
+        _chk(t, torch.float32, nm)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M = a.shape[0]
+    K = a.shape[1] if k is None else k
+    N = w.shape[0] if n is None else n
+    out = out_bf16 if out_bf16 is not None else out_f32
+    assert out is not None and out.stride(1) == 1
+    if out_bf16 is not None and out_f32 is not None:
+        assert out_bf16.stride(0) == out_f32.stride(0)
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if gelu:
+        flags |= EPI_GELU
+    if resid is not None:
+        flags |= EPI_RESIDUAL
+        assert resid.stride(0) == out.stride(0)
+    if ln_sums is not None:
+        flags |= EPI_LNFOLD
+    if stats_out is not None:
+        flags |= EPI_STATS
+    rc = lib().b200vit_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
+                                 out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), float(ln_eps), _ptr(col_s),
+                                 _ptr(stats_out), M, N, K, flags, _stream())
+    _check(rc, "b200vit_gemm_bf16")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor], *,
+              out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+              row_index: Optional[torch.Tensor] = None, eps: float = 1e-5) -> None:
+    _chk(x, torch.float32, "x"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
+    _chk(out_bf16, torch.bfloat16, "out_bf16"); _chk(out_f32, torch.float32, "out_f32")
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = out_bf16 if out_bf16 is not None else out_f32
+    assert out is not None
+    M = out.shape[0]
+    D = x.shape[1]
+    if row_index is not None:
+        assert row_index.dtype == torch.int32 and row_index.numel() == M
+    else:
+        assert x.shape[0] == M
+    rc = lib().b200vit_layernorm(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), _ptr(out_bf16), _ptr(out_f32),
+                                 out.stride(0), _ptr(row_index), M, D, float(eps), _stream())
+    _check(rc, "b200vit_layernorm")
+
+
+def patchify_ln(img: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_bf16: torch.Tensor, ph: int, pw: int,
+                eps: float = 1e-5) -> None:
+    _chk(img, torch.bfloat16, "img"); _chk(out_bf16, torch.bfloat16, "out")
+    _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
+    assert img.is_contiguous() and img.dim() == 4
+    B, Cc, H, W = img.shape
+    rc = lib().b200vit_patchify_ln(_ptr(img), _ptr(gamma), _ptr(beta), _ptr(out_bf16), out_bf16.stride(0), B, Cc, H,
+                                   W, ph, pw, float(eps), _stream())
+    _check(rc, "b200vit_patchify_ln")
+
+
+def embed_tokens(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, cls: Optional[torch.Tensor],
+                 pos: torch.Tensor, x: torch.Tensor, B: int, n: int, ncls: int, eps: float = 1e-5) -> None:
+    for nm, t in (("y", y), ("gamma", gamma), ("beta", beta), ("cls", cls), ("pos", pos), ("x", x)):
+        _chk(t, torch.float32, nm)
+    D = y.shape[1]
+    assert y.is_contiguous() and x.is_contiguous() and pos.is_contiguous()
+    rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), B, n, ncls, D,
+                                    float(eps), _stream())
+    _check(rc, "b200vit_embed_tokens")
+
+
+def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, N: int, H: int, dh: int, scale: float) -> None:
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out")
+    assert qkv.is_contiguous() and out.is_contiguous()
+    assert qkv.shape == (B * N, 3 * H * dh) and out.shape == (B * N, H * dh)
+    rc = lib().b200vit_attention(_ptr(qkv), _ptr(out), B, N, H, dh, float(scale), _stream())
+    _check(rc, "b200vit_attention")
+
+
+def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int) -> None:
+    _chk(x, torch.float32, "x"); _chk(out, torch.float32, "out")
+    assert x.is_contiguous() and out.is_contiguous()
+    rc = lib().b200vit_mean_pool(_ptr(x), _ptr(out), B, N, D, _stream())
+    _check(rc, "b200vit_mean_pool")
+
+
+def cast_f32_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    _chk(x, torch.float32, "x"); _chk(out, torch.bfloat16, "out")
+    assert x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
+    rc = lib().b200vit_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
+    _check(rc, "b200vit_cast_f32_bf16")

@@ -1,0 +1,365 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] * W[N,K]^T)
+//
+//   warp 0        : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1        : MMA issuer    (one thread; tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16, D in TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..11   : epilogue      (tcgen05.ld 32x32b -> registers -> bias / LN-fold / GELU / residual -> global)
+//
+// Two TMEM accumulator stages (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Replaces the nn.Linear call sites listed in include/b200vit.h.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_NON_EPI_THREADS = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = NUM_NON_EPI_THREADS + NUM_EPI_WARPS * 32;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  int flags;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  long long ldo;
+  const float* bias;
+  const float* resid;
+  const float* ln_sums;  // [M][2]
+  float ln_inv_dim;
+  float ln_eps;
+  const float* col_s;  // [N]
+  float* stats_out;    // [M][2]
+};
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256 (power of two)
+  static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "TMEM columns must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= NUM_NON_EPI_THREADS / 32) {
+    // ------------------------------------------------------------------ epilogue
+    const int e = warp - NUM_NON_EPI_THREADS / 32;  // 0..7
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);
+    const int col_off = (e >> 2) * COLS_PER_WARP;
+    const int flags = p.flags;
+    const bool vec_ok = (p.ldo & 7) == 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile % p.num_n_tiles;
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      float mu = 0.f, rstd = 1.f;
+      if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
+        const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
+        mu = ss.x * p.ln_inv_dim;
+        const float var = fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + col_off + c;
+        if (row_ok && col0 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = col0 + j;
+            if (col >= p.N) continue;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+            const bool full8 = (col + 8 <= p.N);
+            if (full8 && vec_ok) {
+              if (flags & B200VIT_EPI_LNFOLD) {
+                const float4 s0 = *reinterpret_cast<const float4*>(p.col_s + col);
+                const float4 s1 = *reinterpret_cast<const float4*>(p.col_s + col + 4);
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = rstd * fmaf(-mu, sv[i], v[i]);
+              }
+              if (flags & B200VIT_EPI_BIAS) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (flags & B200VIT_EPI_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+              }
+              if (flags & B200VIT_EPI_RESIDUAL) {
+                const float* rp = p.resid + (size_t)row * p.ldo + col;
+                const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+              if (p.out_f32) {
+                float* op = p.out_f32 + (size_t)row * p.ldo + col;
+                *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]);
+              pk.w = pack_bf16x2(v[6], v[7]);
+              if (p.out_bf16) *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.ldo + col) = pk;
+              if (flags & B200VIT_EPI_STATS) {
+                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float lo = __uint_as_float(w[i] << 16);
+                  const float hi = __uint_as_float(w[i] & 0xFFFF0000u);
+                  st_sum += lo + hi;
+                  st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+                }
+              }
+            } else {
+              // scalar tail (N or ldo not a multiple of 8)
+              for (int i = 0; i < 8 && col + i < p.N; ++i) {
+                float x = v[i];
+                const int cc = col + i;
+                if (flags & B200VIT_EPI_LNFOLD) x = rstd * fmaf(-mu, p.col_s[cc], x);
+                if (flags & B200VIT_EPI_BIAS) x += p.bias[cc];
+                if (flags & B200VIT_EPI_GELU) x = gelu_erf(x);
+                if (flags & B200VIT_EPI_RESIDUAL) x += p.resid[(size_t)row * p.ldo + cc];
+                if (p.out_f32) p.out_f32[(size_t)row * p.ldo + cc] = x;
+                const __nv_bfloat16 xb = __float2bfloat16_rn(x);
+                if (p.out_bf16) p.out_bf16[(size_t)row * p.ldo + cc] = xb;
+                if (flags & B200VIT_EPI_STATS) {
+                  const float xr = __bfloat162float(xb);
+                  st_sum += xr;
+                  st_sq = fmaf(xr, xr, st_sq);
+                }
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if ((flags & B200VIT_EPI_STATS) && row_ok) {
+        atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
+        atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace b200
+
+extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16,
+                                 float* out_f32, int64_t ldo, const float* bias, const float* resid,
+                                 const float* ln_sums, float ln_eps, const float* col_s, float* stats_out, int M, int N,
+                                 int K, int flags, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(A && W, "gemm: A/W must not be null");
+  B200_CHECK_ARG(out_bf16 || out_f32, "gemm: need at least one output");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                 "gemm: A and W must be 16-byte aligned");
+  B200_CHECK_ARG((lda & 7) == 0 && (ldw & 7) == 0 && lda >= K && ldw >= K,
+                 "gemm: lda=%lld ldw=%lld must be multiples of 8 and >= K=%d", (long long)lda, (long long)ldw, K);
+  B200_CHECK_ARG(ldo >= N, "gemm: ldo=%lld < N=%d", (long long)ldo, N);
+  B200_CHECK_ARG(!(flags & B200VIT_EPI_BIAS) || bias, "gemm: EPI_BIAS without bias");
+  B200_CHECK_ARG(!(flags & B200VIT_EPI_RESIDUAL) || resid, "gemm: EPI_RESIDUAL without resid");
+  B200_CHECK_ARG(!(flags & B200VIT_EPI_LNFOLD) || (ln_sums && col_s), "gemm: EPI_LNFOLD without ln_sums/col_s");
+  B200_CHECK_ARG(!(flags & B200VIT_EPI_STATS) || stats_out, "gemm: EPI_STATS without stats_out");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  B200_CHECK_ARG(al16(bias) && al16(resid) && al16(col_s) && al16(out_bf16) && al16(out_f32) && al16(ln_sums),
+                 "gemm: epilogue pointers must be 16-byte aligned");
+
+  // K-tail: TMA zero-fills out-of-bounds columns of both operands, so any K works as long as rows are 16B multiples.
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.flags = flags;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out_f32 = out_f32;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.resid = resid;
+  p.ln_sums = ln_sums;
+  p.ln_inv_dim = 1.0f / (float)K;
+  p.ln_eps = ln_eps;
+  p.col_s = col_s;
+  p.stats_out = stats_out;
+
+  const bool wide = N > 128;
+  const uint32_t block_n = wide ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)BLOCK_M};
+    int rc = encode_tmap_bf16(&tmA, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)ldw * 2};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, block_n};
+    int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (wide) return launch_gemm<256, 4>(tmA, tmB, p, st);
+  return launch_gemm<128, 6>(tmA, tmB, p, st);
+}

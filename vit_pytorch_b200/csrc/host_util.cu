@@ -1,0 +1,109 @@
+#include "host_util.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_generic(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled could not be resolved (driver too old?)");
+    return B200VIT_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(tm, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return B200VIT_ERR_CUDA;
+  }
+  return 0;
+}
+
+int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, bool swizzle128) {
+  return encode_generic(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return encode_generic(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box,
+                        CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+const char* b200vit_last_error(void) { return b200::g_err; }
+int b200vit_version(void) { return 100; }
+int64_t b200vit_launch_count(void) { return b200::g_launches.load(); }
+void b200vit_reset_launch_count(void) { b200::g_launches.store(0); }
+
+int b200vit_device_ok(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    b200::set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+    return B200VIT_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    b200::set_error("device %d is sm_%d%d; libb200vit contains sm_100a code only", dev, prop.major, prop.minor);
+    return B200VIT_ERR_DEVICE;
+  }
+  if (!b200::get_encode()) {
+    b200::set_error("cuTensorMapEncodeTiled could not be resolved");
+    return B200VIT_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting, launch counting, tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/b200vit.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define B200_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      b200::set_error(__VA_ARGS__);      \
+      return B200VIT_ERR_INVALID;        \
+    }                                    \
+  } while (0)
+
+#define B200_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B200VIT_ERR_CUDA;                                                                    \
+    }                                                                                             \
+  } while (0)
+
+// cuTensorMapEncodeTiled resolved through the runtime (libcuda is only a stub at build time).
+// Encodes a rank-`rank` bf16 tensor map with 128B swizzle.  dims/box innermost first; strides in BYTES for dims 1..
+int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, bool swizzle128 = true);
+int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+int num_sms();
+
+}  // namespace b200

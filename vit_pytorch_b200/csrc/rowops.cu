@@ -1,0 +1,279 @@
+// HBM-bound row kernels around the GEMMs: LayerNorm, patchify + LayerNorm, token assembly, mean pool, cast.
+// One warp per row, float4 / 16-byte accesses, fp32 statistics (two-pass variance, eps inside the sqrt -- the
+// semantics of torch.nn.LayerNorm used at vit.py:19,39,69,101,103).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm: x fp32 [*, D] -> bf16 and/or fp32
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ln_row_stats(const float* __restrict__ xr, int D, int lane, float& mean, float& rstd,
+                                             float eps) {
+  float s = 0.f;
+  if ((D & 3) == 0) {
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) s += xr[i];
+  }
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  if ((D & 3) == 0) {
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + i);
+      const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const float a = xr[i] - mean;
+      q += a * a;
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                 long long ldo, const int* __restrict__ row_index, int M, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long src = row_index ? (long long)row_index[row] : (long long)row;
+  const float* xr = x + src * ldx;
+  float mean, rstd;
+  ln_row_stats(xr, D, lane, mean, rstd, eps);
+  const bool vec = ((D & 3) == 0) && ((ldo & 3) == 0);
+  if (vec) {
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + i);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (beta) b = *reinterpret_cast<const float4*>(beta + i);
+      float4 y;
+      y.x = (v.x - mean) * rstd * g.x + b.x;
+      y.y = (v.y - mean) * rstd * g.y + b.y;
+      y.z = (v.z - mean) * rstd * g.z + b.z;
+      y.w = (v.w - mean) * rstd * g.w + b.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * ldo + i) = y;
+      if (out_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(y.x, y.y);
+        pk.y = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(out_bf16 + (long long)row * ldo + i) = pk;
+      }
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const float y = (xr[i] - mean) * rstd * gamma[i] + (beta ? beta[i] : 0.f);
+      if (out_f32) out_f32[(long long)row * ldo + i] = y;
+      if (out_bf16) out_bf16[(long long)row * ldo + i] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Patchify + LayerNorm(patch_dim).  One CTA per (image, patch row): the C x ph x W pixel slab is staged in smem with
+// coalesced 16-byte loads, then each warp normalises whole patches and writes bf16 rows in (p1 p2 c) order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, int C, int H, int W,
+                   int ph, int pw, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [C][ph][W]
+  const int gh = H / ph, gw = W / pw;
+  const int b = blockIdx.x / gh, h = blockIdx.x % gh;
+  const int slab_elems = C * ph * W;
+  const int row_elems = ph * W;  // contiguous per channel in global memory
+  if ((row_elems & 7) == 0 && ((H * W) & 7) == 0) {
+    for (int i = threadIdx.x * 8; i < slab_elems; i += blockDim.x * 8) {
+      const int c = i / row_elems, r = i % row_elems;
+      const __nv_bfloat16* src = img + ((long long)(b * C + c) * H + (long long)h * ph) * W + r;
+      *reinterpret_cast<uint4*>(slab + i) = *reinterpret_cast<const uint4*>(src);
+    }
+  } else {
+    for (int i = threadIdx.x; i < slab_elems; i += blockDim.x) {
+      const int c = i / row_elems, r = i % row_elems;
+      slab[i] = img[((long long)(b * C + c) * H + (long long)h * ph) * W + r];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pd = ph * pw * C;
+  for (int w = warp; w < gw; w += 8) {
+    // element e = (p1*pw + p2)*C + c  <->  slab[(c*ph + p1)*W + w*pw + p2]
+    float s = 0.f;
+    for (int e = lane; e < pd; e += 32) {
+      const int c = e % C, pp = e / C, p2 = pp % pw, p1 = pp / pw;
+      s += __bfloat162float(slab[(c * ph + p1) * W + w * pw + p2]);
+    }
+    const float mean = warp_sum(s) / (float)pd;
+    float q = 0.f;
+    for (int e = lane; e < pd; e += 32) {
+      const int c = e % C, pp = e / C, p2 = pp % pw, p1 = pp / pw;
+      const float d = __bfloat162float(slab[(c * ph + p1) * W + w * pw + p2]) - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)pd + eps);
+    __nv_bfloat16* orow = out + ((long long)(b * gh + h) * gw + w) * ldo;
+    for (int e = lane; e < (int)ldo; e += 32) {
+      float y = 0.f;
+      if (e < pd) {
+        const int c = e % C, pp = e / C, p2 = pp % pw, p1 = pp / pw;
+        y = (__bfloat162float(slab[(c * ph + p1) * W + w * pw + p2]) - mean) * rstd * gamma[e] + beta[e];
+      }
+      orow[e] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Token assembly: LN(dim) of the patch projection + positional embedding + cls row  -> fp32 residual stream
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int B, int n,
+                    int ncls, int D, float eps) {
+  const int N = n + ncls;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * N) return;
+  const int b = (int)(row / N), t = (int)(row % N);
+  float* xr = x + row * D;
+  const float* pr = pos + (long long)t * D;
+  if (t < ncls) {
+    for (int i = lane; i < D; i += 32) xr[i] = cls[(long long)t * D + i] + pr[i];
+    return;
+  }
+  const float* yr = y + ((long long)b * n + (t - ncls)) * D;
+  float mean, rstd;
+  ln_row_stats(yr, D, lane, mean, rstd, eps);
+  if ((D & 3) == 0) {
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(yr + i);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+      const float4 be = *reinterpret_cast<const float4*>(beta + i);
+      const float4 p = *reinterpret_cast<const float4*>(pr + i);
+      float4 o;
+      o.x = ((v.x - mean) * rstd * g.x + be.x) + p.x;
+      o.y = ((v.y - mean) * rstd * g.y + be.y) + p.y;
+      o.z = ((v.z - mean) * rstd * g.z + be.z) + p.z;
+      o.w = ((v.w - mean) * rstd * g.w + be.w) + p.w;
+      *reinterpret_cast<float4*>(xr + i) = o;
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) xr[i] = ((yr[i] - mean) * rstd * gamma[i] + beta[i]) + pr[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mean_pool_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* xp = x + (long long)b * N * D + d;
+  float s = 0.f;
+  for (int t = 0; t < N; ++t) s += xp[(long long)t * D];
+  out[(long long)b * D + d] = s / (float)N;
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i);
+    const float4 b = *reinterpret_cast<const float4*>(x + i + 4);
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y);
+    pk.y = pack_bf16x2(a.z, a.w);
+    pk.z = pack_bf16x2(b.x, b.y);
+    pk.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + i) = pk;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200vit_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                                 float* out_f32, int64_t ldo, const int32_t* row_index, int M, int D, float eps,
+                                 void* stream) {
+  B200_CHECK_ARG(x && gamma && (out_bf16 || out_f32), "layernorm: null pointer");
+  B200_CHECK_ARG(M > 0 && D > 0 && ldx >= D && ldo >= D, "layernorm: bad shape M=%d D=%d", M, D);
+  B200_CHECK_ARG((ldx & 3) == 0 || (D & 3) != 0, "layernorm: ldx must be a multiple of 4 when D is");
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, ldo, row_index, M, D, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200vit_patchify_ln(const void* img, const float* gamma, const float* beta, void* out_bf16, int64_t ldo,
+                                   int B, int C, int H, int W, int ph, int pw, float eps, void* stream) {
+  B200_CHECK_ARG(img && gamma && beta && out_bf16, "patchify_ln: null pointer");
+  B200_CHECK_ARG(B > 0 && C > 0 && ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0,
+                 "patchify_ln: image %dx%d not divisible by patch %dx%d", H, W, ph, pw);
+  B200_CHECK_ARG(ldo >= (int64_t)C * ph * pw, "patchify_ln: ldo too small");
+  const size_t smem = (size_t)C * ph * W * 2;
+  B200_CHECK_ARG(smem <= 200 * 1024, "patchify_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  patchify_ln_kernel<<<B * (H / ph), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, C, H,
+      W, ph, pw, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls,
+                                    const float* pos, float* x, int B, int n, int ncls, int D, float eps,
+                                    void* stream) {
+  B200_CHECK_ARG(y && gamma && beta && pos && x, "embed_tokens: null pointer");
+  B200_CHECK_ARG(ncls == 0 || cls, "embed_tokens: ncls=%d without cls", ncls);
+  B200_CHECK_ARG(B > 0 && n > 0 && D > 0 && ncls >= 0, "embed_tokens: bad shape");
+  const long long rows = (long long)B * (n + ncls);
+  embed_tokens_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y, gamma, beta, cls, pos, x, B, n, ncls, D, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream) {
+  B200_CHECK_ARG(x && out && B > 0 && N > 0 && D > 0, "mean_pool: bad argument");
+  dim3 grid((D + 255) / 256, B);
+  mean_pool_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, N, D);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream) {
+  B200_CHECK_ARG(x && out_bf16 && n > 0, "cast: bad argument");
+  const long long blocks = (n / 8 + 255) / 256 + 1;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out_bf16), n);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
