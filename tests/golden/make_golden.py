@@ -1,0 +1,94 @@
+"""Generate golden fixtures from the UNMODIFIED reference (lucidrains/vit-pytorch at /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+For each case: build the reference model under torch.manual_seed(seed), round its parameters to bf16-representable
+values (so the same numbers can be fed to the bf16 CUDA path), run the reference forward in fp32 on CPU on a
+bf16-representable input, and additionally run the reference's own bf16 forward (its noise floor).  Saved per case
+(tests/golden/<name>.pt): kind, ctor kwargs, state_dict (bf16), input (bf16), logits_fp32, logits_ref_bf16,
+tokens_fp32 (transformer output for the first sample) and the library versions.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+REF = os.environ.get("VIT_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+from vit_pytorch import ViT, SimpleViT  # noqa: E402  (the reference)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # BASELINE.json configs[0]: SimpleViT tiny (num_classes / mlp_dim chosen in SURVEY.md 8d)
+    "simplevit_tiny": dict(kind="simple", seed=0, batch=4, img=(32, 32),
+                           kwargs=dict(image_size=32, patch_size=4, num_classes=10, dim=192, depth=2, heads=3,
+                                       mlp_dim=768)),
+    # ViT, cls pooling, with biases everywhere, same tiny geometry
+    "vit_tiny_cls": dict(kind="vit", seed=1, batch=3, img=(32, 32),
+                         kwargs=dict(image_size=32, patch_size=4, num_classes=10, dim=192, depth=2, heads=3,
+                                     mlp_dim=768)),
+    # ViT, mean pooling, tuple sizes, smaller non-square input than image_size (README.md:1720-1766), N = 8 tokens
+    "vit_tiny_mean_nonsquare": dict(kind="vit", seed=2, batch=2, img=(32, 16),
+                                    kwargs=dict(image_size=(32, 32), patch_size=(8, 4), num_classes=24, dim=128,
+                                                depth=3, heads=2, mlp_dim=256, pool="mean")),
+    # ViT without head: returns tokens (vit.py:132-133)
+    "vit_tiny_tokens": dict(kind="vit", seed=3, batch=2, img=(32, 32),
+                            kwargs=dict(image_size=32, patch_size=8, num_classes=0, dim=128, depth=1, heads=2,
+                                        mlp_dim=256)),
+}
+
+
+def make(name: str, spec: dict) -> None:
+    torch.manual_seed(spec["seed"])
+    cls = ViT if spec["kind"] == "vit" else SimpleViT
+    model = cls(**spec["kwargs"]).eval()
+    # bf16-representable parameters; perturb LayerNorm affine params so gamma/beta are actually exercised
+    g = torch.Generator().manual_seed(1000 + spec["seed"])
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and ("norm" in n or n.split(".")[-2] in ("0", "1", "3")) and n.endswith("weight"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1 and n.endswith("bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+            p.copy_(p.bfloat16().float())
+    torch.manual_seed(100 + spec["seed"])
+    img = torch.randn(spec["batch"], 3, *spec["img"]).bfloat16()
+    with torch.inference_mode():
+        logits = model(img.float())
+        tokens = None
+        if spec["kind"] == "vit":
+            x = model.to_patch_embedding(img.float()[:1])
+            x = torch.cat((model.cls_token[None], x), dim=1)
+            x = x + model.pos_embedding[: x.shape[1]]
+            tokens = model.transformer(x)
+        model_bf16 = cls(**spec["kwargs"]).eval()
+        model_bf16.load_state_dict(model.state_dict())
+        model_bf16 = model_bf16.bfloat16()
+        logits_bf16 = model_bf16(img)
+    blob = {
+        "name": name,
+        "kind": spec["kind"],
+        "kwargs": spec["kwargs"],
+        "state_dict": {k: v.bfloat16() for k, v in model.state_dict().items()},
+        "input": img,
+        "logits_fp32": logits.clone(),
+        "logits_ref_bf16": logits_bf16.float().clone(),
+        "tokens_fp32": None if tokens is None else tokens.clone(),
+        "versions": {"torch": str(torch.__version__), "reference": "vit-pytorch 1.23.6 @ /root/reference"},
+    }
+    path = os.path.join(HERE, name + ".pt")
+    torch.save(blob, path)
+    print(f"{name}: logits {tuple(logits.shape)} |max| {logits.abs().max():.4f}; "
+          f"ref-bf16 max err {(logits_bf16.float() - logits).abs().max():.5f}; {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    for n, s in CASES.items():
+        make(n, s)

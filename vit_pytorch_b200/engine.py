@@ -1,0 +1,272 @@
+"""Host-side engine of the fused sm_100a forward: weight preparation, workspaces and the kernel schedule.
+
+The nn.Modules in vit.py / simple_vit.py own the parameters (reference-compatible names); this file turns them into
+the flat bf16 / fp32 device buffers the C ABI (include/b200vit.h) consumes and issues the launches on torch's current
+stream.  Nothing here computes on the host and nothing falls back: a missing library or a failing call raises.
+
+Schedule per encoder layer (reference vit.py:78-81), M = B*N token rows, residual stream x kept in fp32:
+    xn  = LayerNorm(x)                         b200vit_layernorm      fp32 -> bf16              (vit.py:52)
+    qkv = xn Wqkv^T                            b200vit_gemm_bf16      tcgen05, bf16 out         (vit.py:54)
+    o   = softmax(q k^T * scale) v             b200vit_attention      tcgen05 + TMEM            (vit.py:55-63)
+    x  += o Wout^T + b                         b200vit_gemm_bf16      residual epilogue, fp32   (vit.py:64,80)
+    xn  = LayerNorm(x)                         b200vit_layernorm                               (vit.py:19)
+    h   = GELU(xn W1^T + b1)                   b200vit_gemm_bf16      bias+GELU epilogue        (vit.py:20-21)
+    x  += h W2^T + b2                          b200vit_gemm_bf16      residual epilogue         (vit.py:23,81)
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_FORCE_EAGER_ENV = "B200VIT_DISABLE_FUSED"
+
+
+def _has_hooks(m: nn.Module) -> bool:
+    return bool(m._forward_hooks) or bool(m._forward_pre_hooks) or bool(getattr(m, "_backward_hooks", None))
+
+
+def hooks_inside(root: nn.Module, skip: Tuple[nn.Module, ...] = ()) -> bool:
+    """True if any submodule strictly inside `root` carries a forward(-pre) hook (Recorder / Extractor style
+    introspection, reference recorder.py:25-30): those need the materialised eager graph."""
+    for m in root.modules():
+        if m is root or any(m is s for s in skip):
+            continue
+        if _has_hooks(m):
+            return True
+    return False
+
+
+def why_not_fused(params: List[torch.Tensor], x: torch.Tensor, *, training: bool, dropout_p: float) -> Optional[str]:
+    """None if the fused path applies to this call, else the reason the eager PyTorch graph is used."""
+    if os.environ.get(_FORCE_EAGER_ENV, "0") == "1":
+        return f"{_FORCE_EAGER_ENV}=1"
+    if not x.is_cuda:
+        return "input is not on a CUDA device"
+    if x.dtype != torch.bfloat16:
+        return f"input dtype {x.dtype} (fused path is bf16)"
+    for p in params:
+        if p.device != x.device:
+            return "parameters and input on different devices"
+        if p.dtype != torch.bfloat16:
+            return f"parameter dtype {p.dtype} (fused path is bf16)"
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return "autograd is recording (fused path is forward only)"
+    if training and dropout_p > 0.0:
+        return "dropout is active"
+    if torch.cuda.get_device_capability(x.device)[0] != 10:
+        return "device is not sm_100"
+    return None
+
+
+class _Prepared:
+    """Flat device buffers derived from one module's parameters + the parameter versions they were built from."""
+
+    def __init__(self) -> None:
+        self.key: Optional[tuple] = None
+        self.t: Dict[str, torch.Tensor] = {}
+
+
+def _version_key(params: List[torch.Tensor]) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+def _f32(p: torch.Tensor) -> torch.Tensor:
+    return p.detach().float().contiguous()
+
+
+def _bf16_rows(p: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """[out, in] weight as contiguous bf16 with the K dim padded to `k_pad` (zeros) for TMA's 16-byte row rule."""
+    w = p.detach()
+    if k_pad is not None and k_pad != w.shape[1]:
+        wp = torch.zeros(w.shape[0], k_pad, device=w.device, dtype=torch.bfloat16)
+        wp[:, : w.shape[1]] = w
+        return wp
+    return w.to(torch.bfloat16).contiguous()
+
+
+class TransformerEngine:
+    """Fused execution of a vit.Transformer / simple_vit.Transformer module (reference vit.py:66-83)."""
+
+    def __init__(self, transformer: nn.Module) -> None:
+        self.mod = transformer
+        self.prep = _Prepared()
+        self.ws_key: Optional[tuple] = None
+        self.ws: Dict[str, torch.Tensor] = {}
+
+    # -------------------------------------------------------------------------------------------- structure
+    def _layers(self):
+        for attn, ff in self.mod.layers:
+            yield attn, ff
+
+    def params(self) -> List[torch.Tensor]:
+        return list(self.mod.parameters())
+
+    def unsupported_reason(self, N: int) -> Optional[str]:
+        for attn, ff in self._layers():
+            if attn.dim_head != 64:
+                return f"dim_head={attn.dim_head} (the attention kernel is built for 64)"
+            if not attn.project_out:
+                return "attention without output projection (heads == 1 and dim_head == dim)"
+            if attn.dim % 8 or ff.hidden_dim % 8:
+                return "dim / mlp_dim not multiples of 8"
+        if N > 512:
+            return f"sequence length {N} > 512 (online-softmax attention not built yet)"
+        return None
+
+    # -------------------------------------------------------------------------------------------- weights
+    def prepared(self) -> Dict[str, torch.Tensor]:
+        params = self.params()
+        key = _version_key(params)
+        if self.prep.key == key:
+            return self.prep.t
+        t: Dict[str, torch.Tensor] = {}
+        for i, (attn, ff) in enumerate(self._layers()):
+            t[f"{i}.ln1.w"], t[f"{i}.ln1.b"] = _f32(attn.norm.weight), _f32(attn.norm.bias)
+            t[f"{i}.qkv.w"] = _bf16_rows(attn.to_qkv.weight)
+            out_lin = attn.out_linear()
+            t[f"{i}.out.w"] = _bf16_rows(out_lin.weight)
+            t[f"{i}.out.b"] = _f32(out_lin.bias) if out_lin.bias is not None else None
+            ln, fc1, fc2 = ff.parts()
+            t[f"{i}.ln2.w"], t[f"{i}.ln2.b"] = _f32(ln.weight), _f32(ln.bias)
+            t[f"{i}.fc1.w"], t[f"{i}.fc1.b"] = _bf16_rows(fc1.weight), _f32(fc1.bias)
+            t[f"{i}.fc2.w"], t[f"{i}.fc2.b"] = _bf16_rows(fc2.weight), _f32(fc2.bias)
+        t["norm.w"], t["norm.b"] = _f32(self.mod.norm.weight), _f32(self.mod.norm.bias)
+        self.prep.key, self.prep.t = key, t
+        return t
+
+    # -------------------------------------------------------------------------------------------- workspaces
+    def workspace(self, M: int, device: torch.device) -> Dict[str, torch.Tensor]:
+        attn0, ff0 = next(iter(self._layers()))
+        D, I, Hd = attn0.dim, attn0.heads * attn0.dim_head, ff0.hidden_dim
+        key = (M, D, I, Hd, device)
+        if self.ws_key != key:
+            bf = dict(device=device, dtype=torch.bfloat16)
+            self.ws = {
+                "xn": torch.empty(M, D, **bf),
+                "qkv": torch.empty(M, 3 * I, **bf),
+                "o": torch.empty(M, I, **bf),
+                "h": torch.empty(M, Hd, **bf),
+            }
+            self.ws_key = key
+        return self.ws
+
+    # -------------------------------------------------------------------------------------------- execution
+    def run_blocks(self, x: torch.Tensor, B: int, N: int) -> None:
+        """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm)."""
+        t = self.prepared()
+        M = B * N
+        ws = self.workspace(M, x.device)
+        for i, (attn, ff) in enumerate(self._layers()):
+            _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"])
+            _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
+            _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+            _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, bias=t[f"{i}.out.b"], resid=x)
+            _lib.layernorm(x, t[f"{i}.ln2.w"], t[f"{i}.ln2.b"], out_bf16=ws["xn"])
+            _lib.gemm(ws["xn"], t[f"{i}.fc1.w"], out_bf16=ws["h"], bias=t[f"{i}.fc1.b"], gelu=True)
+            _lib.gemm(ws["h"], t[f"{i}.fc2.w"], out_f32=x, bias=t[f"{i}.fc2.b"], resid=x)
+
+    def final_norm(self, x: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None,
+                   out_f32: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None) -> None:
+        t = self.prepared()
+        _lib.layernorm(x, t["norm.w"], t["norm.b"], out_bf16=out_bf16, out_f32=out_f32, row_index=row_index)
+
+    def forward_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Transformer.forward on arbitrary bf16 tokens [B, N, D] (what MAE / SimMIM / Distill call,
+        reference mae.py:74, simmim.py:70, distill.py:66)."""
+        B, N, D = tokens.shape
+        x = tokens.reshape(B * N, D).float().contiguous()
+        self.run_blocks(x, B, N)
+        out = torch.empty(B * N, D, device=tokens.device, dtype=torch.bfloat16)
+        self.final_norm(x, out_bf16=out)
+        return out.view(B, N, D)
+
+
+class PatchEmbedEngine:
+    """Fused patch embedding + token assembly (reference vit.py:99-104,120-127 / simple_vit.py:90-95,113-114)."""
+
+    def __init__(self, owner: nn.Module) -> None:
+        self.owner = owner
+        self.prep = _Prepared()
+
+    def params(self) -> List[torch.Tensor]:
+        o = self.owner
+        ps = list(o.to_patch_embedding.parameters())
+        for name in ("cls_token", "pos_embedding"):
+            v = getattr(o, name, None)
+            if isinstance(v, nn.Parameter):
+                ps.append(v)
+        return ps
+
+    def prepared(self, device: torch.device) -> Dict[str, torch.Tensor]:
+        o = self.owner
+        params = self.params()
+        key = _version_key(params) + (str(device),)
+        if self.prep.key == key:
+            return self.prep.t
+        ln1, lin, ln2 = o.to_patch_embedding[1], o.to_patch_embedding[2], o.to_patch_embedding[3]
+        pd = lin.weight.shape[1]
+        kp = (pd + 63) // 64 * 64
+        t = {
+            "ln1.w": _f32(ln1.weight), "ln1.b": _f32(ln1.bias),
+            "w": _bf16_rows(lin.weight, kp), "b": _f32(lin.bias),
+            "ln2.w": _f32(ln2.weight), "ln2.b": _f32(ln2.bias),
+        }
+        t["kp"] = kp  # type: ignore[assignment]
+        cls = getattr(o, "cls_token", None)
+        t["cls"] = _f32(cls) if (cls is not None and cls.shape[0] > 0) else None
+        pos = o.pos_embedding
+        t["pos"] = pos.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.prep.key, self.prep.t = key, t
+        return t
+
+    def run(self, img: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+        """img [B, C, H, W] bf16 -> (x fp32 [B*N, D], B, N)."""
+        o = self.owner
+        ph, pw = o.patch_size
+        B, C, H, W = img.shape
+        if H % ph or W % pw:
+            raise ValueError("Image dimensions must be divisible by the patch size.")
+        t = self.prepared(img.device)
+        n = (H // ph) * (W // pw)
+        ncls = 0 if t["cls"] is None else t["cls"].shape[0]
+        N = n + ncls
+        D = t["w"].shape[0]
+        pos = t["pos"]
+        if pos.shape[0] < N:
+            raise ValueError(f"sequence of {N} tokens exceeds the positional table ({pos.shape[0]})")
+        dev = img.device
+        a0 = torch.empty(B * n, t["kp"], device=dev, dtype=torch.bfloat16)
+        _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw)
+        y = torch.empty(B * n, D, device=dev, dtype=torch.float32)
+        _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
+        x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
+        _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls)
+        return x, B, N
+
+
+class HeadEngine:
+    """Pooled-feature -> logits GEMM (reference vit.py:138 / simple_vit.py:120)."""
+
+    def __init__(self, linear: nn.Linear) -> None:
+        self.lin = linear
+        self.prep = _Prepared()
+
+    def params(self) -> List[torch.Tensor]:
+        return list(self.lin.parameters())
+
+    def run(self, pooled_bf16: torch.Tensor) -> torch.Tensor:
+        params = self.params()
+        key = _version_key(params)
+        if self.prep.key != key:
+            self.prep.t = {"w": _bf16_rows(self.lin.weight),
+                           "b": _f32(self.lin.bias) if self.lin.bias is not None else None}
+            self.prep.key = key
+        t = self.prep.t
+        out = torch.empty(pooled_bf16.shape[0], t["w"].shape[0], device=pooled_bf16.device, dtype=torch.bfloat16)
+        _lib.gemm(pooled_bf16.contiguous(), t["w"], out_bf16=out, bias=t["b"])
+        return out
