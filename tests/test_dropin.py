@@ -1,0 +1,149 @@
+"""Host-side drop-in contract of vit_pytorch_b200.ViT / SimpleViT: constructor signature, state_dict
+layout, attribute surface, eager-graph values against the reference goldens, dispatch rules.  CPU only."""
+import inspect
+
+import pytest
+import torch
+from torch import nn
+
+from conftest import import_reference, load_golden, reference_available
+from vit_pytorch_b200 import SimpleViT, ViT
+from vit_pytorch_b200 import simple_vit as sv_mod
+from vit_pytorch_b200 import vit as vit_mod
+
+
+def _build(g):
+    cls = ViT if g["kind"] == "vit" else SimpleViT
+    m = cls(**g["kwargs"]).eval()
+    m.load_state_dict(g["state_dict"])      # strict: key set and shapes must equal the reference's
+    return m
+
+
+def test_state_dict_layout_equals_reference(golden):
+    cls = ViT if golden["kind"] == "vit" else SimpleViT
+    m = cls(**golden["kwargs"])
+    ours, ref = m.state_dict(), golden["state_dict"]
+    assert list(ours.keys()) == list(ref.keys())          # same names AND same registration order
+    for k in ref:
+        assert ours[k].shape == ref[k].shape, k
+
+
+def test_eager_forward_equals_reference_golden(golden):
+    m = _build(golden).float()
+    with torch.inference_mode():
+        out = m(golden["input"].float())
+    assert torch.allclose(out, golden["logits_fp32"], rtol=1e-5, atol=5e-6)
+
+
+def test_constructor_signatures():
+    sig = inspect.signature(ViT.__init__)
+    names = [p for p in sig.parameters if p != "self"]
+    assert names == ["image_size", "patch_size", "num_classes", "dim", "depth", "heads", "mlp_dim", "pool", "channels",
+                     "dim_head", "dropout", "emb_dropout"]
+    assert all(sig.parameters[n].kind is inspect.Parameter.KEYWORD_ONLY for n in names)
+    assert sig.parameters["pool"].default == "cls" and sig.parameters["dim_head"].default == 64
+    sig = inspect.signature(SimpleViT.__init__)
+    names = [p for p in sig.parameters if p != "self"]
+    assert names == ["image_size", "patch_size", "num_classes", "dim", "depth", "heads", "mlp_dim", "channels",
+                     "dim_head"]
+
+
+def test_assertion_messages():
+    with pytest.raises(AssertionError, match="Image dimensions must be divisible by the patch size."):
+        ViT(image_size=30, patch_size=4, num_classes=2, dim=8, depth=1, heads=1, mlp_dim=8)
+    with pytest.raises(AssertionError, match="pool type must be either cls"):
+        ViT(image_size=32, patch_size=4, num_classes=2, dim=8, depth=1, heads=1, mlp_dim=8, pool="max")
+    with pytest.raises(AssertionError, match="multiple of 4"):
+        SimpleViT(image_size=32, patch_size=4, num_classes=2, dim=6, depth=1, heads=1, mlp_dim=8)
+
+
+def test_attribute_surface():
+    v = ViT(image_size=32, patch_size=(8, 4), num_classes=5, dim=64, depth=2, heads=2, mlp_dim=96, dim_head=16)
+    assert v.patch_size == (8, 4) and v.pool == "cls"
+    assert isinstance(v.to_latent, nn.Identity) and isinstance(v.dropout, nn.Dropout)
+    assert isinstance(v.to_patch_embedding[1], nn.LayerNorm) and isinstance(v.to_patch_embedding[2], nn.Linear)
+    assert v.to_patch_embedding[2].weight.shape == (64, 3 * 8 * 4)
+    assert v.cls_token.shape == (1, 64) and v.pos_embedding.shape == (4 * 8 + 1, 64)
+    attn, ff = v.transformer.layers[1]
+    assert isinstance(attn, vit_mod.Attention) and isinstance(attn.attend, nn.Softmax)
+    assert attn.heads == 2 and attn.scale == 16 ** -0.5
+    assert isinstance(attn.to_out, nn.Sequential) and isinstance(ff.net, nn.Sequential) and len(ff.net) == 6
+    # to_patch_embedding[0] alone is the patchify op (MAE uses it separately, reference mae.py:28-31)
+    img = torch.randn(2, 3, 32, 32)
+    assert v.to_patch_embedding[0](img).shape == (2, 32, 96)
+    s = SimpleViT(image_size=32, patch_size=8, num_classes=5, dim=64, depth=1, heads=2, mlp_dim=96, dim_head=16)
+    assert "pos_embedding" not in s.state_dict() and s.pos_embedding.shape == (16, 64)
+    assert isinstance(s.transformer.layers[0][0].to_out, nn.Linear) and s.transformer.layers[0][0].to_out.bias is None
+    assert len(s.transformer.layers[0][1].net) == 4 and hasattr(s, "linear_head")
+
+
+def test_edge_cases_shapes():
+    # pool='mean' -> no cls token; num_classes=0 -> tokens; heads=1 & dim_head=dim -> Identity projection
+    v = ViT(image_size=32, patch_size=8, num_classes=0, dim=32, depth=1, heads=1, mlp_dim=48, dim_head=32,
+            pool="mean").eval()
+    assert v.cls_token.shape == (0, 32) and v.mlp_head is None
+    assert isinstance(v.transformer.layers[0][0].to_out, nn.Identity)
+    assert v(torch.randn(2, 3, 32, 32)).shape == (2, 16, 32)
+    # smaller, non-square input than image_size (reference README.md:1720-1745)
+    v = ViT(image_size=64, patch_size=16, num_classes=7, dim=32, depth=1, heads=2, mlp_dim=48, dim_head=16).eval()
+    assert v(torch.randn(2, 3, 64, 32)).shape == (2, 7)
+    # the reference's own shape test (tests/test_vit.py:4-20), in train mode with dropout
+    v = ViT(image_size=256, patch_size=32, num_classes=1000, dim=64, depth=2, heads=4, mlp_dim=96, dropout=0.1,
+            emb_dropout=0.1)
+    assert v(torch.randn(1, 3, 256, 256)).shape == (1, 1000)
+
+
+def test_transformer_callable_on_arbitrary_tokens():
+    v = ViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=2, heads=2, mlp_dim=48, dim_head=16).eval()
+    assert v.transformer(torch.randn(2, 5, 32)).shape == (2, 5, 32)     # MAE-style subset of tokens
+
+
+def test_dispatch_reasons_on_cpu():
+    v = ViT(image_size=32, patch_size=8, num_classes=3, dim=128, depth=1, heads=2, mlp_dim=128).eval()
+    img = torch.randn(1, 3, 32, 32)
+    assert v.fused_reason(img) == "input is not on a CUDA device"
+    assert v.transformer.fused_reason(torch.randn(1, 4, 128)) == "input is not on a CUDA device"
+    s = SimpleViT(image_size=32, patch_size=8, num_classes=3, dim=128, depth=1, heads=2, mlp_dim=128).eval()
+    assert s.fused_reason(img) is not None
+
+
+def test_hooks_force_the_observable_graph():
+    from vit_pytorch_b200.engine import hooks_inside
+    v = ViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=1, heads=2, mlp_dim=48, dim_head=16).eval()
+    assert not hooks_inside(v, skip=(v.to_latent,))
+    v.to_latent.register_forward_hook(lambda m, i, o: None)       # Dino-style hook on to_latent is allowed
+    assert not hooks_inside(v, skip=(v.to_latent,))
+    seen = []
+    h = v.transformer.layers[0][0].attend.register_forward_hook(lambda m, i, o: seen.append(o.shape))
+    assert hooks_inside(v, skip=(v.to_latent,)) and hooks_inside(v.transformer)
+    v(torch.randn(2, 3, 32, 32))
+    assert seen == [torch.Size([2, 2, 17, 17])]                    # Recorder-style attention maps (B,H,N,N)
+    h.remove()
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("kind", ["vit", "simple"])
+def test_same_seed_gives_bit_identical_init(kind):
+    ref = import_reference()
+    kwargs = dict(image_size=32, patch_size=8, num_classes=5, dim=64, depth=2, heads=2, mlp_dim=96, dim_head=32)
+    torch.manual_seed(123)
+    a = (ref.ViT if kind == "vit" else ref.SimpleViT)(**kwargs)
+    torch.manual_seed(123)
+    b = (ViT if kind == "vit" else SimpleViT)(**kwargs)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    if kind == "simple":
+        assert torch.equal(a.pos_embedding, b.pos_embedding)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present (GPU box)")
+def test_reference_wrappers_accept_the_dropin():
+    """Recorder / Extractor from the reference operate on our module tree."""
+    import importlib
+    import_reference()
+    Extractor = importlib.import_module("vit_pytorch.extractor").Extractor
+    v = ViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=2, heads=2, mlp_dim=48, dim_head=16).eval()
+    logits, emb = Extractor(v)(torch.randn(2, 3, 32, 32))
+    assert logits.shape == (2, 3) and emb.shape == (2, 17, 32)

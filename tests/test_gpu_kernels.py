@@ -1,0 +1,185 @@
+"""-m gpu: every kernel of libb200vit.so, called through the C ABI, against the oracle's primitives
+(oracle/vit_oracle.py) on the same seeded inputs.  Floating point path: tolerance stated per test."""
+import math
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+from vit_pytorch_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def within(got, ref, rtol=1e-2, atol=1e-3):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).abs() <= atol + rtol * ref.abs()).float().mean().item()
+
+
+def test_device_and_library():
+    assert _lib.device_ok(0)
+    _lib.reset_launch_count()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 256), (591, 1000, 768), (100, 10, 192), (384, 576, 192),
+                                   (1, 768, 768), (130, 264, 72)])
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    out = torch.zeros(M, N, device=DEV)
+    _lib.gemm(a, w, out_f32=out)
+    ref = O.linear(a.float().cpu(), w.float().cpu())
+    # fp32 accumulation of exact bf16 products: only summation order differs from the oracle
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_k_padding_zero_fill():
+    torch.manual_seed(0)
+    a = torch.randn(256, 64, device=DEV).bfloat16()
+    w = torch.randn(192, 64, device=DEV).bfloat16()
+    a[:, 48:] = 7.0                 # garbage beyond K=48 must not be read as data: pass k=48 explicitly
+    w[:, 48:] = 0.0
+    out = torch.zeros(256, 192, device=DEV)
+    _lib.gemm(a, w, out_f32=out, k=48)
+    ref = a[:, :48].float() @ w[:, :48].float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_epilogues_bias_gelu_residual():
+    torch.manual_seed(1)
+    M, N, K = 394, 768, 512
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device=DEV)
+    r = torch.randn(M, N, device=DEV)
+    lin = O.linear(a.float().cpu(), w.float().cpu(), b.cpu())
+    # bias + GELU -> bf16  (FeedForward first half, vit.py:20-21)
+    ob = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(a, w, out_bf16=ob, bias=b, gelu=True)
+    assert within(ob, O.gelu_erf(lin)) > 0.999          # bf16 output rounding only (rtol 1e-2 / atol 1e-3)
+    # bias + residual, in place on the fp32 stream (vit.py:80-81)
+    x = r.clone()
+    _lib.gemm(a, w, out_f32=x, bias=b, resid=x)
+    assert torch.allclose(x.cpu(), lin + r.cpu(), rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_lnfold_and_stats():
+    torch.manual_seed(2)
+    M, N, K = 260, 512, 768
+    a = (torch.randn(M, K, device=DEV) * 2 + 0.3).bfloat16()
+    g = torch.randn(K, device=DEV)
+    be = torch.randn(K, device=DEV)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    wg = (w.float() * g).bfloat16()                         # gamma folded into W, rounded like the product path
+    col_s = wg.float().sum(1)
+    t = w.float() @ be
+    af = a.float()
+    sums = torch.stack([af.sum(1), (af * af).sum(1)], 1).contiguous()
+    out = torch.zeros(M, N, device=DEV)
+    st = torch.zeros(M, 2, device=DEV)
+    ob = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(a, wg, out_f32=out, out_bf16=ob, bias=t.contiguous(), ln_sums=sums, col_s=col_s.contiguous(),
+              stats_out=st)
+    ref = O.linear(O.layer_norm(af.cpu(), g.cpu(), be.cpu()), w.float().cpu())
+    assert within(out, ref) > 0.995                           # extra rounding of gamma*W to bf16
+    rb = ob.float()
+    assert torch.allclose(st[:, 0], rb.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (rb * rb).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,D", [(1000, 768), (77, 50), (513, 1280)])
+def test_layernorm(M, D):
+    torch.manual_seed(3)
+    x = torch.randn(M, D, device=DEV) * 3 + 1
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    of = torch.zeros(M, D, device=DEV)
+    ob = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+    _lib.layernorm(x, g, b, out_bf16=ob, out_f32=of)
+    ref = O.layer_norm(x.cpu(), g.cpu(), b.cpu())
+    assert torch.allclose(of.cpu(), ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(ob.cpu(), of.cpu().bfloat16())
+
+
+def test_layernorm_row_gather_no_bias():
+    torch.manual_seed(4)
+    x = torch.randn(197 * 4, 256, device=DEV)
+    g = torch.randn(256, device=DEV)
+    rows = torch.arange(0, 197 * 4, 197, device=DEV, dtype=torch.int32)
+    of = torch.zeros(4, 256, device=DEV)
+    _lib.layernorm(x, g, None, out_f32=of, row_index=rows)
+    assert torch.allclose(of.cpu(), O.layer_norm(x[rows.long()].cpu(), g.cpu(), None), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,H,W,p", [(3, 224, 224, 16), (3, 32, 32, 4), (3, 224, 224, 14), (1, 64, 32, 8)])
+def test_patchify_ln(C, H, W, p):
+    torch.manual_seed(5)
+    img = torch.randn(3, C, H, W, device=DEV).bfloat16()
+    pd = C * p * p
+    ldo = (pd + 63) // 64 * 64
+    g, b = torch.randn(pd, device=DEV), torch.randn(pd, device=DEV)
+    out = torch.full((3 * (H // p) * (W // p), ldo), 7.0, device=DEV, dtype=torch.bfloat16)
+    _lib.patchify_ln(img, g, b, out, p, p)
+    ref = O.layer_norm(O.patchify(img.float().cpu(), p, p), g.cpu(), b.cpu()).reshape(-1, pd)
+    assert torch.equal(out[:, :pd].cpu(), ref.bfloat16()) or within(out[:, :pd], ref) > 0.9999
+    assert (out[:, pd:] == 0).all()
+
+
+@pytest.mark.parametrize("ncls", [0, 1])
+def test_embed_tokens(ncls):
+    torch.manual_seed(6)
+    B, n, D = 3, 49, 192
+    y = torch.randn(B * n, D, device=DEV)
+    g, be = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    cls = torch.randn(ncls, D, device=DEV) if ncls else None
+    pos = torch.randn(n + ncls, D, device=DEV)
+    x = torch.zeros(B * (n + ncls), D, device=DEV)
+    _lib.embed_tokens(y, g, be, cls, pos, x, B, n, ncls)
+    t = O.layer_norm(y.cpu(), g.cpu(), be.cpu()).view(B, n, D)
+    if ncls:
+        t = torch.cat([cls.cpu()[None].expand(B, -1, -1), t], 1)
+    assert torch.allclose(x.cpu(), (t + pos.cpu()[None]).reshape(-1, D), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,H", [(4, 197, 12), (3, 64, 3), (2, 257, 16), (5, 50, 4), (2, 16, 2), (2, 129, 2),
+                                   (1, 512, 1), (2, 1, 2)])
+def test_attention(B, N, H):
+    torch.manual_seed(N)
+    dh = 64
+    I = H * dh
+    qkv = torch.randn(B * N, 3 * I, device=DEV).bfloat16()
+    out = torch.zeros(B * N, I, device=DEV, dtype=torch.bfloat16)
+    _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+    q, k, v = qkv.float().cpu().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = (O.softmax_last((q @ k.transpose(-1, -2)) * dh ** -0.5) @ v).permute(0, 2, 1, 3).reshape(B * N, I)
+    # bf16 P and bf16 output: rtol 1e-2 / atol 1e-3 per element, allow 0.5 % stragglers
+    assert within(out, ref) > 0.995
+    assert (out.float().cpu() - ref).abs().max() < 2e-2
+
+
+def test_attention_large_logits_are_stable():
+    torch.manual_seed(9)
+    B, N, H, dh = 2, 197, 2, 64
+    qkv = (torch.randn(B * N, 3 * H * dh, device=DEV) * 6).bfloat16()      # |s| up to ~300: softmax nearly one-hot
+    out = torch.zeros(B * N, H * dh, device=DEV, dtype=torch.bfloat16)
+    _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+    assert torch.isfinite(out.float()).all()
+    q, k, v = qkv.float().cpu().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = (O.softmax_last((q @ k.transpose(-1, -2)) * dh ** -0.5) @ v).permute(0, 2, 1, 3).reshape(B * N, H * dh)
+    assert within(out, ref, rtol=2e-2, atol=2e-2) > 0.99
+
+
+def test_mean_pool_and_cast():
+    torch.manual_seed(10)
+    x = torch.randn(8, 197, 768, device=DEV)
+    o = torch.zeros(8, 768, device=DEV)
+    _lib.mean_pool(x, o, 8, 197, 768)
+    assert torch.allclose(o.cpu(), x.cpu().mean(1), rtol=1e-5, atol=1e-6)
+    xb = torch.zeros(x.numel(), device=DEV, dtype=torch.bfloat16)
+    _lib.cast_f32_bf16(x.view(-1), xb)
+    assert torch.equal(xb.cpu(), x.view(-1).cpu().bfloat16())
+
+
+def test_kernels_were_launched_by_the_library():
+    assert _lib.launch_count() > 0

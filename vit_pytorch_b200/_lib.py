@@ -85,6 +85,43 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# optional per-call CUDA-event timing (bench.py's roofline pass); None = off (the normal, un-instrumented path)
+# ------------------------------------------------------------------------------------------------------------------
+_prof: Optional[list] = None
+
+
+def profile_start() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_stop() -> list:
+    """Returns [(kernel, meta, milliseconds), ...] for every library call since profile_start()."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [(name, meta, e0.elapsed_time(e1)) for name, meta, e0, e1 in rec]
+
+
+class _Timed:
+    def __init__(self, name: str, **meta) -> None:
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.e1.record()
+            _prof.append((self.name, self.meta, self.e0, self.e1))
+        return False
+
+
 def launch_count() -> int:
     return int(lib().b200vit_launch_count())
 
@@ -134,9 +171,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
         flags |= EPI_LNFOLD
     if stats_out is not None:
         flags |= EPI_STATS
-    rc = lib().b200vit_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
-                                 out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), float(ln_eps), _ptr(col_s),
-                                 _ptr(stats_out), M, N, K, flags, _stream())
+    with _Timed("gemm", M=M, N=N, K=K, flags=flags, flops=2.0 * M * N * K):
+        rc = lib().b200vit_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
+                                     out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), float(ln_eps),
+                                     _ptr(col_s), _ptr(stats_out), M, N, K, flags, _stream())
     _check(rc, "b200vit_gemm_bf16")
 
 
@@ -154,8 +192,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor]
         assert row_index.dtype == torch.int32 and row_index.numel() == M
     else:
         assert x.shape[0] == M
-    rc = lib().b200vit_layernorm(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), _ptr(out_bf16), _ptr(out_f32),
-                                 out.stride(0), _ptr(row_index), M, D, float(eps), _stream())
+    nbytes = M * D * (4 + (2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
+    with _Timed("layernorm", M=M, D=D, bytes=nbytes):
+        rc = lib().b200vit_layernorm(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), _ptr(out_bf16), _ptr(out_f32),
+                                     out.stride(0), _ptr(row_index), M, D, float(eps), _stream())
     _check(rc, "b200vit_layernorm")
 
 
@@ -165,8 +205,9 @@ def patchify_ln(img: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_
     _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
     assert img.is_contiguous() and img.dim() == 4
     B, Cc, H, W = img.shape
-    rc = lib().b200vit_patchify_ln(_ptr(img), _ptr(gamma), _ptr(beta), _ptr(out_bf16), out_bf16.stride(0), B, Cc, H,
-                                   W, ph, pw, float(eps), _stream())
+    with _Timed("patchify_ln", bytes=img.numel() * 2 + out_bf16.numel() * 2):
+        rc = lib().b200vit_patchify_ln(_ptr(img), _ptr(gamma), _ptr(beta), _ptr(out_bf16), out_bf16.stride(0), B, Cc,
+                                       H, W, ph, pw, float(eps), _stream())
     _check(rc, "b200vit_patchify_ln")
 
 
@@ -176,8 +217,9 @@ def embed_tokens(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, cls: 
         _chk(t, torch.float32, nm)
     D = y.shape[1]
     assert y.is_contiguous() and x.is_contiguous() and pos.is_contiguous()
-    rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), B, n, ncls, D,
-                                    float(eps), _stream())
+    with _Timed("embed_tokens", bytes=(y.numel() + x.numel()) * 4):
+        rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), B, n, ncls,
+                                        D, float(eps), _stream())
     _check(rc, "b200vit_embed_tokens")
 
 
@@ -185,19 +227,22 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, N: int, H: int, dh: 
     _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out")
     assert qkv.is_contiguous() and out.is_contiguous()
     assert qkv.shape == (B * N, 3 * H * dh) and out.shape == (B * N, H * dh)
-    rc = lib().b200vit_attention(_ptr(qkv), _ptr(out), B, N, H, dh, float(scale), _stream())
+    with _Timed("attention", B=B, N=N, H=H, bytes=(qkv.numel() + out.numel()) * 2, flops=4.0 * B * H * N * N * dh):
+        rc = lib().b200vit_attention(_ptr(qkv), _ptr(out), B, N, H, dh, float(scale), _stream())
     _check(rc, "b200vit_attention")
 
 
 def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int) -> None:
     _chk(x, torch.float32, "x"); _chk(out, torch.float32, "out")
     assert x.is_contiguous() and out.is_contiguous()
-    rc = lib().b200vit_mean_pool(_ptr(x), _ptr(out), B, N, D, _stream())
+    with _Timed("mean_pool", bytes=x.numel() * 4):
+        rc = lib().b200vit_mean_pool(_ptr(x), _ptr(out), B, N, D, _stream())
     _check(rc, "b200vit_mean_pool")
 
 
 def cast_f32_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
     _chk(x, torch.float32, "x"); _chk(out, torch.bfloat16, "out")
     assert x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
-    rc = lib().b200vit_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
+    with _Timed("cast", bytes=x.numel() * 6):
+        rc = lib().b200vit_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
     _check(rc, "b200vit_cast_f32_bf16")
