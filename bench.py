@@ -166,7 +166,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     model = ViT(**VIT_B16).eval().to(dev, torch.bfloat16)
     torch.manual_seed(1 + rank)
     img = torch.randn(B, 3, 224, 224, device=dev).bfloat16()
-    assert model.fused_reason(img) is None, model.fused_reason(img)
+    with torch.inference_mode():
+        assert model.fused_reason(img) is None, model.fused_reason(img)
 
     def step(x):
         with torch.inference_mode():

@@ -29,9 +29,9 @@ def stats(got, ref):
 def test_fused_path_is_selected_and_counts_launches(golden):
     m = fused_model(golden)
     img = golden["input"].to(DEV)
-    assert m.fused_reason(img) is None
     _lib.reset_launch_count()
     with torch.inference_mode():
+        assert m.fused_reason(img) is None
         m(img)
     torch.cuda.synchronize()
     depth = golden["kwargs"]["depth"]
@@ -68,8 +68,8 @@ def test_transformer_on_arbitrary_tokens_fused():
     sd = O.upcast(g["state_dict"])
     torch.manual_seed(5)
     tok = torch.randn(3, 23, 192).bfloat16()
-    assert m.transformer.fused_reason(tok.to(DEV)) is None
     with torch.inference_mode():
+        assert m.transformer.fused_reason(tok.to(DEV)) is None
         out = m.transformer(tok.to(DEV))
     ref = O.transformer(sd, tok.float(), 2, 3, "vit")
     assert stats(out, ref)[2] > 0.98
