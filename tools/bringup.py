@@ -33,9 +33,10 @@ def _err(got, ref):
 
 
 def case_gemm(M, N, K, bias=False, gelu=False, resid=False, f32=False, both=False, lnfold=False, stats=False,
-              lda=None):
+              lda=None, force=0, inplace=False):
     import torch
     from vit_pytorch_b200 import _lib
+    _lib.lib().b200vit_debug_set(4, force)
     torch.manual_seed(0)
     dev = "cuda"
     lda = lda or K
@@ -64,20 +65,29 @@ def case_gemm(M, N, K, bias=False, gelu=False, resid=False, f32=False, both=Fals
     if resid:
         ref = ref + r
     st = torch.zeros(M, 2, device=dev) if stats else None
-    _lib.gemm(a, w, out_bf16=out_bf16, out_f32=out_f32, bias=b, resid=r, gelu=gelu, ln_sums=ln_sums, col_s=col_s,
-              stats_out=st)
-    torch.cuda.synchronize()
+    if inplace:
+        out_f32 = r.clone()
+        _lib.gemm(a, w, out_f32=out_f32, bias=b, resid=out_f32)
+        torch.cuda.synchronize()
+        out_f32_first = out_f32.clone()
+        r_arg = out_f32
+    else:
+        r_arg = r
+        _lib.gemm(a, w, out_bf16=out_bf16, out_f32=out_f32, bias=b, resid=r, gelu=gelu, ln_sums=ln_sums, col_s=col_s,
+                  stats_out=st)
+        torch.cuda.synchronize()
     res = {}
     if out_bf16 is not None:
         res["bf16"] = _err(out_bf16, ref)
     if out_f32 is not None:
-        res["f32"] = _err(out_f32, ref)
+        res["f32"] = _err(out_f32_first if inplace else out_f32, ref)
     if stats:
         rb = ref.bfloat16().float()
         res["stats_sum"] = _err(st[:, 0], rb.sum(1))
         res["stats_sq"] = _err(st[:, 1], (rb * rb).sum(1))
     # timing
     if M * N * K > 1e9:
+        r = r_arg
         for _ in range(3):
             _lib.gemm(a, w, out_bf16=out_bf16, out_f32=out_f32, bias=b, resid=r, gelu=gelu, ln_sums=ln_sums,
                       col_s=col_s)
@@ -248,9 +258,21 @@ CASES = {
     "gemm_ragged": lambda: case_gemm(197 * 3, 1000, 768, bias=True),
     "gemm_tail10": lambda: case_gemm(100, 10, 192, bias=True, f32=True),
     "gemm_k48pad": lambda: case_gemm(256, 192, 48, lda=64),
+    "g2_min": lambda: case_gemm(256, 256, 64, force=2),
+    "g2_k768": lambda: case_gemm(512, 512, 768, force=2),
+    "g2_3pairs": lambda: case_gemm(768, 768, 256, bias=True, force=2),
+    "g2_ragged": lambda: case_gemm(591, 1000, 768, bias=True, force=2),
+    "g2_gelu": lambda: case_gemm(1024, 3072, 768, bias=True, gelu=True, force=2),
+    "g2_lnfold": lambda: case_gemm(1024, 2304, 768, lnfold=True, force=2),
+    "g2_f32": lambda: case_gemm(1024, 768, 768, bias=True, f32=True, force=2),
+    "g2_resid": lambda: case_gemm(1100, 768, 3072, bias=True, resid=True, f32=True, force=2),
+    "g2_resid_inplace": lambda: case_gemm(2048, 768, 768, bias=True, resid=True, f32=True, force=2, inplace=True),
+    "g2_many_tiles": lambda: case_gemm(20000, 768, 512, bias=True, resid=True, f32=True, force=2, inplace=True),
+    "gemm_big_qkv_v1": lambda: case_gemm(100864, 2304, 768, force=1),
     "gemm_big_qkv": lambda: case_gemm(100864, 2304, 768),
     "gemm_big_fc1": lambda: case_gemm(100864, 3072, 768, bias=True, gelu=True),
-    "gemm_big_fc2": lambda: case_gemm(100864, 768, 3072, bias=True, resid=True, f32=True),
+    "gemm_big_fc2": lambda: case_gemm(100864, 768, 3072, bias=True, resid=True, f32=True, inplace=True),
+    "gemm_big_outproj": lambda: case_gemm(100864, 768, 768, bias=True, resid=True, f32=True, inplace=True),
     "gemm_big_out": lambda: case_gemm(100864, 768, 768, bias=True, resid=True, both=True, stats=True),
     "ln_768": lambda: case_layernorm(1000, 768),
     "ln_nobeta_idx": lambda: case_layernorm(999, 1024, beta=False, idx=True),

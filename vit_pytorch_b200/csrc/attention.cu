@@ -88,8 +88,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  const int q_tiles = (p.N + 127) / 128;
-
   if (warp == TMA_WARP) {
     // ---------------------------------------------------------------- producer
     if (lane == 0) {
@@ -181,60 +179,108 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int h = bh % p.H, b = bh / p.H;
       const int qrow = (round * NWG + t) * 128 + r_in_tile;
 
+      // warps whose 32 query rows all lie beyond N skip the arithmetic but keep the barrier protocol in lockstep
+      const bool warp_active = (round * NWG + t) * 128 + quad * 32 < p.N;
+
       mbar_wait(&s_full[t], up);
       tc_fence_after();
-      // pass 1: row max over the valid keys
-      float mx = -INFINITY;
-      for (int c0 = 0; c0 < p.KP; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_lane + c0, r);
-        tmem_ld_wait();
-        if (c0 + 16 <= p.N) {
+      float sum = 1.f;
+      if (warp_active) {
+        const int n_chunks = (p.KP + 31) >> 5;  // 32-column chunks; the last one may be 16 wide
+        // chunk loader: x32, or x16 for a 16-wide tail (upper half then holds stale values that the col < N mask drops)
+        auto load_chunk = [&](uint32_t (&r)[32], int ci) {
+          const int c0 = ci << 5;
+          if (c0 + 32 <= p.KP) {
+            tmem_ld_32x32b_x32(t_lane + c0, r);
+          } else {
+            uint32_t lo[16];
+            tmem_ld_32x32b_x16(t_lane + c0, lo);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-        } else {
+            for (int j = 0; j < 16; ++j) r[j] = lo[j];
+          }
+        };
+        uint32_t ra[32], rb[32];
+        // ---- pass 1: row max over the valid keys (software pipelined: next chunk's tcgen05.ld in flight)
+        float mx = -INFINITY;
+        auto max_chunk = [&](const uint32_t (&r)[32], int ci) {
+          const int c0 = ci << 5;
+          if (c0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.N) mx = fmaxf(mx, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.N) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
+        };
+        load_chunk(ra, 0);
+        for (int ci = 0; ci < n_chunks; ci += 2) {
+          tmem_ld_wait();
+          if (ci + 1 < n_chunks) load_chunk(rb, ci + 1);
+          max_chunk(ra, ci);
+          if (ci + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (ci + 2 < n_chunks) load_chunk(ra, ci + 2);
+            max_chunk(rb, ci + 1);
+          }
         }
-      }
-      const float mc = mx * c;
-      // pass 2: p = exp2(s*c - max*c), row sum, P -> TMEM (aliasing S) or smem
-      float sum = 0.f;
-      for (int c0 = 0; c0 < p.KP; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_lane + c0, r);
-        tmem_ld_wait();
-        float pv[16];
-        if (c0 + 16 <= p.N) {
+        const float mc = mx * c;
+        // ---- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S, or swizzled smem
+        sum = 0.f;
+        auto exp_chunk = [&](const uint32_t (&r)[32], int ci) {
+          const int c0 = ci << 5;
+          float pv[32];
+          if (c0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pv[j] = exp2f(fmaf(__uint_as_float(r[j]), c, -mc));
-        } else {
+            for (int j = 0; j < 32; ++j) pv[j] = fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pv[j] = (c0 + j < p.N) ? exp2f(fmaf(__uint_as_float(r[j]), c, -mc)) : 0.f;
-        }
-        uint32_t pk[8];
+            for (int j = 0; j < 32; ++j)
+              pv[j] = (c0 + j < p.N) ? fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc)) : 0.f;
+          }
+          uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sum += pv[2 * j] + pv[2 * j + 1];
-          pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) {
+            sum += pv[2 * j] + pv[2 * j + 1];
+            pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
+          }
+          const bool full = c0 + 32 <= p.KP;
+          if (PSMEM) {
+            uint8_t* prow = p_smem + t * p_tile_bytes + (c0 >> 6) * (128 * 128) + (r_in_tile >> 3) * 1024 +
+                            (r_in_tile & 7) * 128;
+            const int jj = (c0 & 63) >> 3;
+            const int sw7 = r_in_tile & 7;
+            *reinterpret_cast<uint4*>(prow + (((jj) ^ sw7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(prow + (((jj + 1) ^ sw7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (full) {
+              *reinterpret_cast<uint4*>(prow + (((jj + 2) ^ sw7) << 4)) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+              *reinterpret_cast<uint4*>(prow + (((jj + 3) ^ sw7) << 4)) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+            }
+          } else if (full) {
+            tmem_st_32x32b_x16(t_lane + (c0 >> 1), pk);
+          } else {
+            uint32_t pk8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
+            tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk8);
+          }
+        };
+        load_chunk(ra, 0);
+        for (int ci = 0; ci < n_chunks; ci += 2) {
+          tmem_ld_wait();
+          if (ci + 1 < n_chunks) load_chunk(rb, ci + 1);
+          exp_chunk(ra, ci);
+          if (ci + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (ci + 2 < n_chunks) load_chunk(ra, ci + 2);
+            exp_chunk(rb, ci + 1);
+          }
         }
         if (PSMEM) {
-          // row r, keys c0..c0+15 -> chunk c0/64, two 16-byte pieces jj = (c0%64)/8 + {0,1}, swizzled by (row & 7)
-          uint8_t* prow = p_smem + t * p_tile_bytes + (c0 >> 6) * (128 * 128) + (r_in_tile >> 3) * 1024 +
-                          (r_in_tile & 7) * 128;
-          const int jj = (c0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(prow + (((jj) ^ (r_in_tile & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(prow + (((jj + 1) ^ (r_in_tile & 7)) << 4)) =
-              make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          fence_proxy_async_smem();
         } else {
-          tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk);
+          tmem_st_wait();
         }
-      }
-      if (PSMEM) {
-        fence_proxy_async_smem();
-      } else {
-        tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
@@ -244,31 +290,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
-      uint32_t o[64];
-      {
-        uint32_t r0[32], r1[32];
+      uint32_t r0[32], r1[32];
+      if (warp_active) {
         tmem_ld_32x32b_x32(t_lane + O_COL, r0);
         tmem_ld_32x32b_x32(t_lane + O_COL + 32, r1);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          o[j] = r0[j];
-          o[32 + j] = r1[j];
-        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
-      if (qrow < p.N) {
+      if (warp_active && qrow < p.N) {
         __nv_bfloat16* op = p.out + ((size_t)b * p.N + qrow) * p.I + h * ATT_DH;
 #pragma unroll
-        for (int j = 0; j < 64; j += 8) {
+        for (int j = 0; j < 32; j += 8) {
           uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-          pk.y = pack_bf16x2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-          pk.z = pack_bf16x2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-          pk.w = pack_bf16x2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+          pk.x = pack_bf16x2(__uint_as_float(r0[j]) * inv, __uint_as_float(r0[j + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv, __uint_as_float(r0[j + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv, __uint_as_float(r0[j + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv, __uint_as_float(r0[j + 7]) * inv);
           *reinterpret_cast<uint4*>(op + j) = pk;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(r1[j]) * inv, __uint_as_float(r1[j + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv, __uint_as_float(r1[j + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv, __uint_as_float(r1[j + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv, __uint_as_float(r1[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + 32 + j) = pk;
         }
       }
     }
@@ -312,6 +361,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 1: g_attn_psmem = value; return 0;
     case 2: g_attn_v_lbo = value; return 0;
     case 3: g_attn_v_sbo = value; return 0;
+    case 4: gemm_force_version(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }
@@ -352,17 +402,21 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
     if (rc) return rc;
   }
   const bool psmem = g_attn_psmem != 0;
-  const int stages = psmem ? 1 : 2;
   const size_t kv_bytes = (size_t)att_kv_bytes(p.kv_boxes, p.kv_box_rows);
   const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * 128 * 128;
   const size_t p_bytes = psmem ? (size_t)nwg * ((p.KP + 63) / 64) * 128 * 128 : 0;
-  const size_t smem_bytes = stages * stage_bytes + p_bytes + (2 * stages + 4 * nwg) * 8 + 16 + 1024;
+  auto smem_for = [&](int st) { return st * stage_bytes + p_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
+  // two K/V/Q stages when they fit (prefetch of the next unit), else one
+  const int stages = (!psmem && smem_for(2) <= 227 * 1024) ? 2 : 1;
+  const size_t smem_bytes = smem_for(stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (nwg == 2) {
     if (psmem) return launch_attention<2, 1, true>(tmQ, tmKV, p, smem_bytes, st);
+    if (stages == 1) return launch_attention<2, 1, false>(tmQ, tmKV, p, smem_bytes, st);
     return launch_attention<2, 2, false>(tmQ, tmKV, p, smem_bytes, st);
   }
   if (psmem) return launch_attention<1, 1, true>(tmQ, tmKV, p, smem_bytes, st);
+  if (stages == 1) return launch_attention<1, 1, false>(tmQ, tmKV, p, smem_bytes, st);
   return launch_attention<1, 2, false>(tmQ, tmKV, p, smem_bytes, st);
 }

@@ -327,6 +327,11 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   B200_CHECK_ARG(al16(bias) && al16(resid) && al16(col_s) && al16(out_bf16) && al16(out_f32) && al16(ln_sums),
                  "gemm: epilogue pointers must be 16-byte aligned");
 
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (gemm2_eligible(M, N, K, ldo, flags, out_bf16, out_f32, resid))
+    return launch_gemm2(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_eps, col_s, M, N, K, flags,
+                        st);
+
   // K-tail: TMA zero-fills out-of-bounds columns of both operands, so any K works as long as rows are 16B multiples.
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
@@ -359,7 +364,6 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (wide) return launch_gemm<256, 4>(tmA, tmB, p, st);
   return launch_gemm<128, 6>(tmA, tmB, p, st);
 }

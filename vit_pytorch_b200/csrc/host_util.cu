@@ -64,9 +64,9 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, bool swizzle128) {
   return encode_generic(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box,
-                        CU_TENSOR_MAP_SWIZZLE_NONE);
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int num_sms() {

@@ -37,7 +37,15 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, bool swizzle128 = true);
 int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box);
+                    const uint32_t* box, bool swizzle128 = false);
+
+// gemm2.cu (CTA-pair kernel)
+int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_bf16, const float* out_f32,
+                   const float* resid);
+int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
+                 const float* bias, const float* resid, const float* ln_sums, float ln_eps, const float* col_s, int M,
+                 int N, int K, int flags, cudaStream_t stream);
+void gemm_force_version(int v);
 
 int num_sms();
 
