@@ -49,6 +49,7 @@ int b200vit_device_ok(int dev);
  *   simple_vit.py:30,32,47,48,93,108.
  * out_bf16 and/or out_f32 (either may be NULL, not both), row stride ldo (elements).
  * EPI_LNFOLD: ln_sums[M][2] = per-row (sum, sum of squares) of A, ln_dim = K, col_s[N] = sum_k W[n,k] (fp32).
+ * EPI_STATS:  stats_out[M][2] is zeroed by the call, then receives (sum, sum of squares) of the bf16-rounded rows.
  * Requirements: A, W 16-byte aligned, lda, ldw multiples of 8, K multiple of 8.
  */
 int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32,
@@ -77,11 +78,17 @@ int b200vit_patchify_ln(const void* img, const float* gamma, const float* beta, 
  * Token assembly after the patch projection: y[B*n, D] (fp32, patch GEMM output incl. bias) ->
  *   x[b, t, :] = LN_D(y[b, t - ncls, :]) * gamma + beta + pos[t, :]   for t >= ncls
  *   x[b, 0, :] = cls[:] + pos[0, :]                                    if ncls == 1
- * written as the fp32 residual stream x[B*(n+ncls), D].
+ * written as the fp32 residual stream x[B*(n+ncls), D].  Optional (may be NULL): xb_bf16 = bf16 copy of x and
+ * stats[M][2] = per-row (sum, sum of squares) of that copy -- the inputs of the first LN-folded GEMM.
  * Replaces nn.LayerNorm(dim) vit.py:103, cls concat vit.py:122-123, pos add vit.py:125-127 (simple_vit.py:94,114).
  */
 int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls, const float* pos,
-                         float* x, int B, int n, int ncls, int D, float eps, void* stream);
+                         float* x, void* xb_bf16, float* stats, int B, int n, int ncls, int D, float eps,
+                         void* stream);
+
+/* x[M, D] fp32 -> xb bf16 copy + stats[M][2] = (sum, sum of squares) of the bf16-rounded rows: entry into the
+ * LN-folded layer chain for token matrices handed to Transformer.forward directly (reference mae.py:74). */
+int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, int D, void* stream);
 
 /*
  * Multi-head softmax attention straight out of the packed QKV buffer:

@@ -268,6 +268,9 @@ CASES = {
     "g2_resid": lambda: case_gemm(1100, 768, 3072, bias=True, resid=True, f32=True, force=2),
     "g2_resid_inplace": lambda: case_gemm(2048, 768, 768, bias=True, resid=True, f32=True, force=2, inplace=True),
     "g2_many_tiles": lambda: case_gemm(20000, 768, 512, bias=True, resid=True, f32=True, force=2, inplace=True),
+    "g2_dual": lambda: case_gemm(2048, 768, 768, bias=True, resid=True, both=True, stats=True, force=2),
+    "gemm_big_out_dual": lambda: case_gemm(100864, 768, 768, bias=True, resid=True, both=True, stats=True),
+    "gemm_big_fc2_dual": lambda: case_gemm(100864, 768, 3072, bias=True, resid=True, both=True, stats=True),
     "gemm_big_qkv_v1": lambda: case_gemm(100864, 2304, 768, force=1),
     "gemm_big_qkv": lambda: case_gemm(100864, 2304, 768),
     "gemm_big_fc1": lambda: case_gemm(100864, 3072, 768, bias=True, gelu=True),

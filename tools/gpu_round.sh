@@ -11,7 +11,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_bench_${TAG}.log 2>&1
 tail -3 gpurun_out/launches_${TAG}.csv | cut -c1-300
 echo "== ncu full (gemm)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 8 -c 4 -f -o gpurun_out/prof_gemm_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX:-gemm} -s ${KSKIP:-8} -c ${KCOUNT:-5} -f -o gpurun_out/prof_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_full_${TAG}.log
 ls -la gpurun_out/
 fi

@@ -25,7 +25,7 @@ EPI_STATS = 16
 SYMBOLS = [
     "b200vit_last_error", "b200vit_version", "b200vit_launch_count", "b200vit_reset_launch_count",
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
-    "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16",
+    "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -60,7 +60,11 @@ def lib() -> C.CDLL:
     L.b200vit_patchify_ln.restype = i32
     L.b200vit_patchify_ln.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_embed_tokens.restype = i32
-    L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_rowstats_cast.restype = i32
+    L.b200vit_rowstats_cast.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.b200vit_debug_set.restype = i32
+    L.b200vit_debug_set.argtypes = [i32, i32]
     L.b200vit_attention.restype = i32
     L.b200vit_attention.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     L.b200vit_mean_pool.restype = i32
@@ -212,15 +216,26 @@ def patchify_ln(img: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_
 
 
 def embed_tokens(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, cls: Optional[torch.Tensor],
-                 pos: torch.Tensor, x: torch.Tensor, B: int, n: int, ncls: int, eps: float = 1e-5) -> None:
+                 pos: torch.Tensor, x: torch.Tensor, B: int, n: int, ncls: int, eps: float = 1e-5,
+                 xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
+    _chk(xb, torch.bfloat16, "xb"); _chk(stats, torch.float32, "stats")
     for nm, t in (("y", y), ("gamma", gamma), ("beta", beta), ("cls", cls), ("pos", pos), ("x", x)):
         _chk(t, torch.float32, nm)
     D = y.shape[1]
     assert y.is_contiguous() and x.is_contiguous() and pos.is_contiguous()
     with _Timed("embed_tokens", bytes=(y.numel() + x.numel()) * 4):
-        rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), B, n, ncls,
-                                        D, float(eps), _stream())
+        rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), _ptr(xb),
+                                        _ptr(stats), B, n, ncls, D, float(eps), _stream())
     _check(rc, "b200vit_embed_tokens")
+
+
+def rowstats_cast(x: torch.Tensor, xb: torch.Tensor, stats: torch.Tensor) -> None:
+    _chk(x, torch.float32, "x"); _chk(xb, torch.bfloat16, "xb"); _chk(stats, torch.float32, "stats")
+    assert x.is_contiguous() and xb.is_contiguous() and stats.is_contiguous()
+    M, D = x.shape
+    with _Timed("rowstats_cast", bytes=M * D * 6):
+        rc = lib().b200vit_rowstats_cast(_ptr(x), _ptr(xb), _ptr(stats), M, D, _stream())
+    _check(rc, "b200vit_rowstats_cast")
 
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, N: int, H: int, dh: int, scale: float) -> None:

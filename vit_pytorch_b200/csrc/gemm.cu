@@ -329,8 +329,8 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (gemm2_eligible(M, N, K, ldo, flags, out_bf16, out_f32, resid))
-    return launch_gemm2(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_eps, col_s, M, N, K, flags,
-                        st);
+    return launch_gemm2(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_eps, col_s, stats_out, M, N,
+                        K, flags, st);
 
   // K-tail: TMA zero-fills out-of-bounds columns of both operands, so any K works as long as rows are 16B multiples.
   GemmParams p{};
@@ -364,6 +364,7 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
+  if (flags & B200VIT_EPI_STATS) B200_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * sizeof(float), st));
   if (wide) return launch_gemm<256, 4>(tmA, tmB, p, st);
   return launch_gemm<128, 6>(tmA, tmB, p, st);
 }

@@ -25,19 +25,25 @@ namespace g2 {
 constexpr int BLOCK_M = 128;       // rows per CTA (256 per pair)
 constexpr int BLOCK_N = 256;       // columns per tile (each CTA stages 128 W rows)
 constexpr int BLOCK_K = 64;
-constexpr int STAGES = 5;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int EPI_BUF_BYTES = 4096;                   // one 32-row x 128-byte swizzled box
-constexpr int EPI_BYTES = NUM_EPI_WARPS * 2 * EPI_BUF_BYTES;
-constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_BYTES;
-// full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[8][2] + tmem ptr
-constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
-constexpr int DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 constexpr int COLS_PER_WARP = BLOCK_N / 2;            // 128
+// DUAL (fp32 residual stream in place + bf16 copy + row statistics) needs a third staging box per warp, paid for
+// with one pipeline stage: 4 x 32 KB + 96 KB instead of 5 x 32 KB + 64 KB.
+template <bool DUAL>
+struct Cfg {
+  static constexpr int STAGES = DUAL ? 4 : 5;
+  static constexpr int BUFS_PER_WARP = DUAL ? 3 : 2;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * BUFS_PER_WARP * EPI_BUF_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_BYTES;
+  // full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[8][2] + tmem ptr
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
+  static constexpr int DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
 }  // namespace g2
 
 struct Gemm2Params {
@@ -49,13 +55,18 @@ struct Gemm2Params {
   const float* ln_sums;
   float ln_inv_dim, ln_eps;
   const float* col_s;
+  float* stats_out;  // DUAL: [M][2] (sum, sum of squares) of the bf16-rounded output rows, accumulated atomically
 };
 
+template <bool DUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmResid,
-             const Gemm2Params p) {
+             const __grid_constant__ CUtensorMap tmOutB, const Gemm2Params p) {
   using namespace g2;
+  using C = Cfg<DUAL>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int BAR_OFFSET = C::BAR_OFFSET;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
@@ -168,7 +179,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int col_off = (e >> 2) * COLS_PER_WARP;
     const int flags = p.flags;
     const bool has_resid = (flags & B200VIT_EPI_RESIDUAL) != 0;
-    uint8_t* buf0 = epi_smem + e * 2 * EPI_BUF_BYTES;
+    uint8_t* buf0 = epi_smem + e * C::BUFS_PER_WARP * EPI_BUF_BYTES;
+    uint8_t* bbuf = buf0 + 2 * EPI_BUF_BYTES;  // DUAL only: bf16 copy staging box (64 columns)
+    float st_sum = 0.f, st_sq = 0.f;
     uint64_t* rbar = resid_full + 2 * e;
     const uint32_t tmem_empty_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
@@ -216,6 +229,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mu = ss.x * p.ln_inv_dim;
         rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
       }
+      if (DUAL) st_sum = st_sq = 0.f;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
@@ -270,6 +284,31 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               float4 x = *sp;
               x.x += v[4 * q]; x.y += v[4 * q + 1]; x.z += v[4 * q + 2]; x.w += v[4 * q + 3];
               *sp = x;
+              if (DUAL) {
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+              }
+            }
+            if (DUAL) {
+              // bf16 copy of the new residual rows (A operand of the next, LN-folded GEMM) + its row statistics
+              const int half = (c >> 5) & 1;
+              uint8_t* brow = bbuf + lane * 128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
+                pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+                pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4)) = pk;
+                const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float lo = __uint_as_float(w4[i] << 16);
+                  const float hi = __uint_as_float(w4[i] & 0xFFFF0000u);
+                  st_sum += lo + hi;
+                  st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+                }
+              }
             }
           } else {
             if (lane == 0) tma_store_wait_read<1>();
@@ -285,6 +324,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int cc, cr;
             box_coords(tile, c >> 5, cc, cr);
             tma_store_2d(&tmOut, buf0 + (box_seq & 1) * EPI_BUF_BYTES, cc, cr);
+            if (DUAL && ((c >> 5) & 1)) tma_store_2d(&tmOutB, bbuf, cc - 32, cr);
             tma_store_commit();
           }
           if (has_resid) {
@@ -327,6 +367,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (DUAL && row_ok) {
+        atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
+        atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -351,9 +395,15 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
                    const float* resid) {
   (void)K;
   if (g_gemm_force == 1) return 0;
-  if (flags & B200VIT_EPI_STATS) return 0;                 // dual-output + stats epilogue lives in v1 for now
-  if (out_bf16 && out_f32) return 0;
-  if (out_bf16 && (flags & B200VIT_EPI_RESIDUAL)) return 0;
+  const bool dual = out_bf16 && out_f32;
+  if (dual) {
+    // fp32 stream (in place, residual) + bf16 copy + statistics: the LN-fold producer epilogue
+    if (!(flags & B200VIT_EPI_RESIDUAL) || !(flags & B200VIT_EPI_STATS) || (flags & B200VIT_EPI_GELU)) return 0;
+    if ((ldo % 8) != 0 || (N % 64) != 0) return 0;
+  } else {
+    if (flags & B200VIT_EPI_STATS) return 0;
+  }
+  if (!dual && out_bf16 && (flags & B200VIT_EPI_RESIDUAL)) return 0;
   if (out_f32 && (flags & B200VIT_EPI_GELU)) return 0;
   if (out_bf16 && (ldo % 8) != 0) return 0;                // TMA: 16-byte row pitch
   if (out_f32 && (ldo % 4) != 0) return 0;
@@ -363,11 +413,30 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
   return (M >= 1024 && N >= 256) ? 1 : 0;                  // small problems: the single-CTA kernel has finer tiles
 }
 
-int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
-                 const float* bias, const float* resid, const float* ln_sums, float ln_eps, const float* col_s, int M,
-                 int N, int K, int flags, cudaStream_t stream) {
+template <bool DUAL>
+static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmResid, const CUtensorMap& tmOutB, const Gemm2Params& p, int clusters,
+                          cudaStream_t stream) {
   using namespace g2;
+  auto kern = gemm2_kernel<DUAL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<DUAL>::DYN_BYTES));
+    attr_set = true;
+  }
+  kern<<<2 * clusters, NUM_THREADS, Cfg<DUAL>::DYN_BYTES, stream>>>(tmA, tmB, tmOut, tmResid, tmOutB, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
+                 const float* bias, const float* resid, const float* ln_sums, float ln_eps, const float* col_s,
+                 float* stats_out, int M, int N, int K, int flags, cudaStream_t stream) {
+  using namespace g2;
+  const bool dual = out_bf16 && out_f32;
   Gemm2Params p{};
+  p.stats_out = stats_out;
   p.M = M; p.N = N; p.K = K;
   p.num_m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   p.num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
@@ -380,7 +449,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.ln_eps = ln_eps;
   p.col_s = col_s;
 
-  CUtensorMap tmA, tmB, tmOut, tmResid;
+  CUtensorMap tmA, tmB, tmOut, tmResid, tmOutB;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)lda * 2};
@@ -403,6 +472,13 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
     if (rc) return rc;
     rc = encode_tmap_f32(&tmResid, resid ? resid : out_f32, 2, dims, strides, box, true);
     if (rc) return rc;
+    tmOutB = tmOut;
+    if (dual) {
+      const uint64_t bstrides[1] = {(uint64_t)ldo * 2};
+      const uint32_t bbox[2] = {64, 32};
+      rc = encode_tmap_bf16(&tmOutB, out_bf16, 2, dims, bstrides, bbox);
+      if (rc) return rc;
+    }
   } else {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)ldo * 2};
@@ -410,19 +486,16 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
     int rc = encode_tmap_bf16(&tmOut, out_bf16, 2, dims, strides, box);
     if (rc) return rc;
     tmResid = tmOut;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
-    attr_set = true;
+    tmOutB = tmOut;
   }
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_kernel<<<2 * clusters, NUM_THREADS, DYN_BYTES, stream>>>(tmA, tmB, tmOut, tmResid, p);
-  B200_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  if (dual) {
+    B200_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * sizeof(float), stream));
+    return launch_gemm2_t<true>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+  }
+  return launch_gemm2_t<false>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
 }
 
 void gemm_force_version(int v) { g_gemm_force = v; }

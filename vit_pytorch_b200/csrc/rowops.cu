@@ -144,37 +144,104 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_tokens_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int B, int n,
-                    int ncls, int D, float eps) {
+                    const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                    __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int B, int n, int ncls, int D,
+                    float eps) {
   const int N = n + ncls;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * N) return;
   const int b = (int)(row / N), t = (int)(row % N);
   float* xr = x + row * D;
+  __nv_bfloat16* xbr = xb ? xb + row * D : nullptr;
   const float* pr = pos + (long long)t * D;
+  float s1 = 0.f, s2 = 0.f;  // sum / sum of squares of the bf16-rounded row (LN-fold statistics for the first layer)
+  auto emit = [&](int i, float v) {
+    xr[i] = v;
+    const __nv_bfloat16 vb = __float2bfloat16_rn(v);
+    if (xbr) xbr[i] = vb;
+    const float vr = __bfloat162float(vb);
+    s1 += vr;
+    s2 = fmaf(vr, vr, s2);
+  };
   if (t < ncls) {
-    for (int i = lane; i < D; i += 32) xr[i] = cls[(long long)t * D + i] + pr[i];
-    return;
+    for (int i = lane; i < D; i += 32) emit(i, cls[(long long)t * D + i] + pr[i]);
+  } else {
+    const float* yr = y + ((long long)b * n + (t - ncls)) * D;
+    float mean, rstd;
+    ln_row_stats(yr, D, lane, mean, rstd, eps);
+    if ((D & 3) == 0) {
+      for (int i = lane * 4; i < D; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(yr + i);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+        const float4 be = *reinterpret_cast<const float4*>(beta + i);
+        const float4 p = *reinterpret_cast<const float4*>(pr + i);
+        float4 o;
+        o.x = ((v.x - mean) * rstd * g.x + be.x) + p.x;
+        o.y = ((v.y - mean) * rstd * g.y + be.y) + p.y;
+        o.z = ((v.z - mean) * rstd * g.z + be.z) + p.z;
+        o.w = ((v.w - mean) * rstd * g.w + be.w) + p.w;
+        *reinterpret_cast<float4*>(xr + i) = o;
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        if (xbr) *reinterpret_cast<uint2*>(xbr + i) = pk;
+        const float a0 = __uint_as_float(pk.x << 16), a1 = __uint_as_float(pk.x & 0xFFFF0000u);
+        const float a2 = __uint_as_float(pk.y << 16), a3 = __uint_as_float(pk.y & 0xFFFF0000u);
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+      }
+    } else {
+      for (int i = lane; i < D; i += 32) emit(i, ((yr[i] - mean) * rstd * gamma[i] + beta[i]) + pr[i]);
+    }
   }
-  const float* yr = y + ((long long)b * n + (t - ncls)) * D;
-  float mean, rstd;
-  ln_row_stats(yr, D, lane, mean, rstd, eps);
+  if (stats) {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      stats[2 * row] = s1;
+      stats[2 * row + 1] = s2;
+    }
+  }
+}
+
+// fp32 rows -> bf16 copy + (sum, sum of squares) of the bf16-rounded row: entry into the LN-folded layer chain for
+// token matrices that do not come from embed_tokens (Transformer called directly on tokens).
+__global__ void __launch_bounds__(256)
+rowstats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int M,
+                     int D) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + row * D;
+  __nv_bfloat16* br = xb + row * D;
+  float s1 = 0.f, s2 = 0.f;
   if ((D & 3) == 0) {
     for (int i = lane * 4; i < D; i += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(yr + i);
-      const float4 g = *reinterpret_cast<const float4*>(gamma + i);
-      const float4 be = *reinterpret_cast<const float4*>(beta + i);
-      const float4 p = *reinterpret_cast<const float4*>(pr + i);
-      float4 o;
-      o.x = ((v.x - mean) * rstd * g.x + be.x) + p.x;
-      o.y = ((v.y - mean) * rstd * g.y + be.y) + p.y;
-      o.z = ((v.z - mean) * rstd * g.z + be.z) + p.z;
-      o.w = ((v.w - mean) * rstd * g.w + be.w) + p.w;
-      *reinterpret_cast<float4*>(xr + i) = o;
+      const float4 v = *reinterpret_cast<const float4*>(xr + i);
+      uint2 pk;
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(br + i) = pk;
+      const float a0 = __uint_as_float(pk.x << 16), a1 = __uint_as_float(pk.x & 0xFFFF0000u);
+      const float a2 = __uint_as_float(pk.y << 16), a3 = __uint_as_float(pk.y & 0xFFFF0000u);
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
     }
   } else {
-    for (int i = lane; i < D; i += 32) xr[i] = ((yr[i] - mean) * rstd * gamma[i] + beta[i]) + pr[i];
+    for (int i = lane; i < D; i += 32) {
+      const __nv_bfloat16 vb = __float2bfloat16_rn(xr[i]);
+      br[i] = vb;
+      const float vr = __bfloat162float(vb);
+      s1 += vr;
+      s2 = fmaf(vr, vr, s2);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    stats[2 * row] = s1;
+    stats[2 * row + 1] = s2;
   }
 }
 
@@ -245,15 +312,24 @@ extern "C" int b200vit_patchify_ln(const void* img, const float* gamma, const fl
   return 0;
 }
 
+extern "C" int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, int D, void* stream) {
+  B200_CHECK_ARG(x && xb_bf16 && stats && M > 0 && D > 0, "rowstats_cast: bad argument");
+  rowstats_cast_kernel<<<(M + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, M, D);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 extern "C" int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls,
-                                    const float* pos, float* x, int B, int n, int ncls, int D, float eps,
-                                    void* stream) {
+                                    const float* pos, float* x, void* xb_bf16, float* stats, int B, int n, int ncls,
+                                    int D, float eps, void* stream) {
   B200_CHECK_ARG(y && gamma && beta && pos && x, "embed_tokens: null pointer");
   B200_CHECK_ARG(ncls == 0 || cls, "embed_tokens: ncls=%d without cls", ncls);
   B200_CHECK_ARG(B > 0 && n > 0 && D > 0 && ncls >= 0, "embed_tokens: bad shape");
   const long long rows = (long long)B * (n + ncls);
   embed_tokens_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      y, gamma, beta, cls, pos, x, B, n, ncls, D, eps);
+      y, gamma, beta, cls, pos, x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, B, n, ncls, D, eps);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

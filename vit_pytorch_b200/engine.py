@@ -24,6 +24,18 @@ from torch import nn
 from . import _lib
 
 _FORCE_EAGER_ENV = "B200VIT_DISABLE_FUSED"
+_LN_MODE_ENV = "B200VIT_LN_MODE"      # "fold" (default) | "exact"
+
+
+def ln_mode() -> str:
+    """'fold'  : no standalone LayerNorm kernels inside the layer loop.  The residual GEMMs (out-proj, fc2) also emit
+                 a bf16 copy of x plus per-row (sum, sum^2); the following GEMM multiplies that copy by gamma*W and
+                 applies  rstd*(acc - mu*colsum) + (W beta + b)  in its epilogue.
+       'exact' : LayerNorm kernel -> bf16 -> GEMM, the literal operator sequence of the reference."""
+    m = os.environ.get(_LN_MODE_ENV, "fold")
+    if m not in ("fold", "exact"):
+        raise ValueError(f"{_LN_MODE_ENV} must be 'fold' or 'exact', got {m!r}")
+    return m
 
 
 def _has_hooks(m: nn.Module) -> bool:
@@ -125,9 +137,21 @@ class TransformerEngine:
         if self.prep.key == key:
             return self.prep.t
         t: Dict[str, torch.Tensor] = {}
+
+        def fold(prefix: str, lin_w: torch.Tensor, lin_b: Optional[torch.Tensor], g: torch.Tensor, b: torch.Tensor):
+            # LN(x) W^T + bias  ==  rstd * (x (gamma*W)^T - mu * colsum) + (W beta + bias)
+            w32 = lin_w.detach().float()
+            wg = (w32 * g.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+            t[prefix + ".wg"] = wg
+            t[prefix + ".s"] = wg.float().sum(dim=1).contiguous()          # from the ROUNDED weights the MMA sees
+            tb = w32 @ b.detach().float()
+            t[prefix + ".t"] = (tb + lin_b.detach().float() if lin_b is not None else tb).contiguous()
+
         for i, (attn, ff) in enumerate(self._layers()):
             t[f"{i}.ln1.w"], t[f"{i}.ln1.b"] = _f32(attn.norm.weight), _f32(attn.norm.bias)
             t[f"{i}.qkv.w"] = _bf16_rows(attn.to_qkv.weight)
+            fold(f"{i}.qkv", attn.to_qkv.weight, None, attn.norm.weight, attn.norm.bias)
+            fold(f"{i}.fc1", ff.parts()[1].weight, ff.parts()[1].bias, ff.parts()[0].weight, ff.parts()[0].bias)
             out_lin = attn.out_linear()
             t[f"{i}.out.w"] = _bf16_rows(out_lin.weight)
             t[f"{i}.out.b"] = _f32(out_lin.bias) if out_lin.bias is not None else None
@@ -147,20 +171,40 @@ class TransformerEngine:
         if self.ws_key != key:
             bf = dict(device=device, dtype=torch.bfloat16)
             self.ws = {
-                "xn": torch.empty(M, D, **bf),
+                "xn": torch.empty(M, D, **bf),          # exact: LayerNorm output; fold: bf16 copy of x
                 "qkv": torch.empty(M, 3 * I, **bf),
                 "o": torch.empty(M, I, **bf),
                 "h": torch.empty(M, Hd, **bf),
+                "stats_a": torch.empty(M, 2, device=device, dtype=torch.float32),
+                "stats_b": torch.empty(M, 2, device=device, dtype=torch.float32),
             }
             self.ws_key = key
         return self.ws
 
     # -------------------------------------------------------------------------------------------- execution
-    def run_blocks(self, x: torch.Tensor, B: int, N: int) -> None:
-        """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm)."""
+    def run_blocks(self, x: torch.Tensor, B: int, N: int, primed: bool = False) -> None:
+        """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm).
+
+        fold mode needs ws['xn'] (bf16 copy of x) and ws['stats_a'] (row sums of that copy) on entry: `primed` says
+        the caller (embed_tokens) already wrote them, otherwise one rowstats_cast pass produces them."""
         t = self.prepared()
         M = B * N
         ws = self.workspace(M, x.device)
+        if ln_mode() == "fold":
+            xb, sa, sb = ws["xn"], ws["stats_a"], ws["stats_b"]
+            if not primed:
+                _lib.rowstats_cast(x, xb, sa)
+            for i, (attn, ff) in enumerate(self._layers()):
+                _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"], ln_sums=sa,
+                          col_s=t[f"{i}.qkv.s"])
+                _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+                _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
+                          stats_out=sb)
+                _lib.gemm(xb, t[f"{i}.fc1.wg"], out_bf16=ws["h"], bias=t[f"{i}.fc1.t"], gelu=True, ln_sums=sb,
+                          col_s=t[f"{i}.fc1.s"])
+                _lib.gemm(ws["h"], t[f"{i}.fc2.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.fc2.b"], resid=x,
+                          stats_out=sa)
+            return
         for i, (attn, ff) in enumerate(self._layers()):
             _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"])
             _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
@@ -224,8 +268,9 @@ class PatchEmbedEngine:
         self.prep.key, self.prep.t = key, t
         return t
 
-    def run(self, img: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-        """img [B, C, H, W] bf16 -> (x fp32 [B*N, D], B, N)."""
+    def run(self, img: torch.Tensor, xb: Optional[torch.Tensor] = None,
+            stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:
+        """img [B, C, H, W] bf16 -> (x fp32 [B*N, D], B, N); optionally also the bf16 copy of x and its row sums."""
         o = self.owner
         ph, pw = o.patch_size
         B, C, H, W = img.shape
@@ -245,8 +290,15 @@ class PatchEmbedEngine:
         y = torch.empty(B * n, D, device=dev, dtype=torch.float32)
         _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
         x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
-        _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls)
+        _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls, xb=xb, stats=stats)
         return x, B, N
+
+    def geometry(self, img: torch.Tensor) -> Tuple[int, int]:
+        """(B, N) the image batch will produce, without running anything."""
+        ph, pw = self.owner.patch_size
+        cls = getattr(self.owner, "cls_token", None)
+        ncls = cls.shape[0] if cls is not None else 0
+        return img.shape[0], (img.shape[2] // ph) * (img.shape[3] // pw) + ncls
 
 
 class HeadEngine:

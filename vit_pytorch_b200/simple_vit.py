@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, why_not_fused
+from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode, why_not_fused
 from .vit import Patchify, pair
 
 
@@ -178,9 +178,13 @@ class SimpleViT(nn.Module):
         if self._patch_engine is None:
             self._patch_engine = PatchEmbedEngine(self)
         eng = self.transformer.engine()
-        x, B, N = self._patch_engine.run(img)
+        B, N = self._patch_engine.geometry(img)
+        primed = ln_mode() == "fold"
+        ws = eng.workspace(B * N, img.device) if primed else None
+        x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
+                                         stats=ws["stats_a"] if primed else None)
         D = x.shape[1]
-        eng.run_blocks(x, B, N)
+        eng.run_blocks(x, B, N, primed=primed)
         dev = img.device
         xf = torch.empty_like(x)
         eng.final_norm(x, out_f32=xf)

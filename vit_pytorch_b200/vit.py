@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, why_not_fused
+from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode, why_not_fused
 
 
 def pair(t):
@@ -218,9 +218,13 @@ class ViT(nn.Module):
         if self._patch_engine is None:
             self._patch_engine = PatchEmbedEngine(self)
         eng = self.transformer.engine()
-        x, B, N = self._patch_engine.run(img)          # fp32 residual stream [B*N, D]
+        B, N = self._patch_engine.geometry(img)
+        primed = ln_mode() == "fold"
+        ws = eng.workspace(B * N, img.device) if primed else None
+        x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
+                                         stats=ws["stats_a"] if primed else None)   # fp32 residual stream [B*N, D]
         D = x.shape[1]
-        eng.run_blocks(x, B, N)
+        eng.run_blocks(x, B, N, primed=primed)
         dev = img.device
         if self.mlp_head is None:                      # reference vit.py:132-133: return the normalised tokens
             out = torch.empty(B * N, D, device=dev, dtype=torch.bfloat16)
