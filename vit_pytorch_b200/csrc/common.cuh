@@ -249,7 +249,8 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the only data this arrive orders are TMEM reads, already fenced by tcgen05.fence::before_thread_sync
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completes its bytes on the mbarrier at `bar_cluster_addr`
 // (the leader CTA's barrier), data lands in the issuing CTA's own shared memory.
