@@ -7,7 +7,7 @@
 //   TMA warp   : K[KP,64], V[KP,64], Q[128,64] x NWG  -> 128B-swizzled smem (3-D tensor map => rows >= N are zero)
 //   MMA thread : S_t = Q_t K^T           tcgen05.mma 128 x KP x 64      -> TMEM region t (fp32, KP columns)
 //   softmax WG : thread == query row (tcgen05.ld 32x32b): row max, p = exp2((s-max)*scale*log2e), row sum,
-//                P as bf16 back into TMEM (aliasing S, FA4 style)  [or into swizzled smem: PSMEM variant]
+//                P as packed bf16 back into TMEM (aliasing S, FA4 style)
 //   MMA thread : O_t = P_t V             tcgen05.mma 128 x 64 x KP, A from TMEM, B = V as MN-major smem operand
 //   softmax WG : O / rowsum -> bf16 -> out[b, row, h*64 : h*64+64]
 //
@@ -34,7 +34,7 @@ struct AttnParams {
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
 
-template <int NWG, int STAGES, bool PSMEM>
+template <int NWG, int STAGES>
 __global__ void __launch_bounds__((4 * NWG + 2) * 32, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttnParams p) {
@@ -47,10 +47,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_bytes = att_kv_bytes(p.kv_boxes, p.kv_box_rows);  // multiple of 1024
   const int stage_bytes = 2 * kv_bytes + NWG * Q_TILE_BYTES;
-  const int p_chunks = (p.KP + 63) / 64;
-  const int p_tile_bytes = PSMEM ? p_chunks * 128 * 128 : 0;
-  uint8_t* p_smem = smem + STAGES * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + NWG * p_tile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* s_full = empty_bar + STAGES;
@@ -151,13 +148,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int k = 0; k < ksteps; ++k) {
             // 16 keys = two 8-row groups of V = 2048 B
             const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
-            if (PSMEM) {
-              // P tile in smem: K-major, 64-key chunks of [128 rows x 128 B]
-              const uint32_t pa = smem_u32(p_smem + t * p_tile_bytes) + (k >> 2) * (128 * 128) + (k & 3) * 32;
-              umma_ss(d_o, make_smem_desc_sw128(pa, 16, 1024), vdesc, idesc_pv, k != 0);
-            } else {
-              umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
-            }
+            umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);  // A = P from TMEM
           }
           umma_commit(&o_full[t]);
         }
@@ -186,101 +177,90 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       float sum = 1.f;
       if (warp_active) {
-        const int n_chunks = (p.KP + 31) >> 5;  // 32-column chunks; the last one may be 16 wide
-        // chunk loader: x32, or x16 for a 16-wide tail (upper half then holds stale values that the col < N mask drops)
-        auto load_chunk = [&](uint32_t (&r)[32], int ci) {
-          const int c0 = ci << 5;
-          if (c0 + 32 <= p.KP) {
-            tmem_ld_32x32b_x32(t_lane + c0, r);
-          } else {
-            uint32_t lo[16];
-            tmem_ld_32x32b_x16(t_lane + c0, lo);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = lo[j];
-          }
-        };
+        // Columns [0, 32*nfull) need no key mask; the rest (< 48 columns) is handled 16 at a time with the mask.
+        const int nfull = p.N >> 5;
         uint32_t ra[32], rb[32];
-        // ---- pass 1: row max over the valid keys (software pipelined: next chunk's tcgen05.ld in flight)
-        float mx = -INFINITY;
-        auto max_chunk = [&](const uint32_t (&r)[32], int ci) {
-          const int c0 = ci << 5;
-          if (c0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.N) mx = fmaxf(mx, __uint_as_float(r[j]));
-          }
-        };
-        load_chunk(ra, 0);
-        for (int ci = 0; ci < n_chunks; ci += 2) {
+        // ---------------- pass 1: row max (4 independent chains; next chunk's tcgen05.ld in flight)
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#define ATT_MAX32(R)                                                    \
+  _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                   \
+    m0 = fmaxf(m0, __uint_as_float(R[j]));                              \
+    m1 = fmaxf(m1, __uint_as_float(R[j + 1]));                          \
+    m2 = fmaxf(m2, __uint_as_float(R[j + 2]));                          \
+    m3 = fmaxf(m3, __uint_as_float(R[j + 3]));                          \
+  }
+        int ci = 0;
+        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
+        for (; ci + 1 < nfull; ci += 2) {
           tmem_ld_wait();
-          if (ci + 1 < n_chunks) load_chunk(rb, ci + 1);
-          max_chunk(ra, ci);
-          if (ci + 1 < n_chunks) {
-            tmem_ld_wait();
-            if (ci + 2 < n_chunks) load_chunk(ra, ci + 2);
-            max_chunk(rb, ci + 1);
-          }
-        }
-        const float mc = mx * c;
-        // ---- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S, or swizzled smem
-        sum = 0.f;
-        auto exp_chunk = [&](const uint32_t (&r)[32], int ci) {
-          const int c0 = ci << 5;
-          float pv[32];
-          if (c0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pv[j] = fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              pv[j] = (c0 + j < p.N) ? fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc)) : 0.f;
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            sum += pv[2 * j] + pv[2 * j + 1];
-            pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
-          }
-          const bool full = c0 + 32 <= p.KP;
-          if (PSMEM) {
-            uint8_t* prow = p_smem + t * p_tile_bytes + (c0 >> 6) * (128 * 128) + (r_in_tile >> 3) * 1024 +
-                            (r_in_tile & 7) * 128;
-            const int jj = (c0 & 63) >> 3;
-            const int sw7 = r_in_tile & 7;
-            *reinterpret_cast<uint4*>(prow + (((jj) ^ sw7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(prow + (((jj + 1) ^ sw7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            if (full) {
-              *reinterpret_cast<uint4*>(prow + (((jj + 2) ^ sw7) << 4)) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-              *reinterpret_cast<uint4*>(prow + (((jj + 3) ^ sw7) << 4)) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
-            }
-          } else if (full) {
-            tmem_st_32x32b_x16(t_lane + (c0 >> 1), pk);
-          } else {
-            uint32_t pk8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
-            tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk8);
-          }
-        };
-        load_chunk(ra, 0);
-        for (int ci = 0; ci < n_chunks; ci += 2) {
+          tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
+          ATT_MAX32(ra)
           tmem_ld_wait();
-          if (ci + 1 < n_chunks) load_chunk(rb, ci + 1);
-          exp_chunk(ra, ci);
-          if (ci + 1 < n_chunks) {
-            tmem_ld_wait();
-            if (ci + 2 < n_chunks) load_chunk(ra, ci + 2);
-            exp_chunk(rb, ci + 1);
+          if (ci + 2 < nfull) tmem_ld_32x32b_x32(t_lane + (ci + 2) * 32, ra);
+          ATT_MAX32(rb)
+        }
+        if (ci < nfull) {
+          tmem_ld_wait();
+          ATT_MAX32(ra)
+        }
+        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
+          uint32_t r16[16];
+          tmem_ld_32x32b_x16(t_lane + c0, r16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.N) m0 = fmaxf(m0, __uint_as_float(r16[j]));
+        }
+        const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+        // ---------------- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#define ATT_EXP32(R, C0)                                                                      \
+  {                                                                                           \
+    uint32_t pk[16];                                                                          \
+    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                       \
+      const float e0 = fast_ex2(fmaf(__uint_as_float(R[j]), c, -mc));                         \
+      const float e1 = fast_ex2(fmaf(__uint_as_float(R[j + 1]), c, -mc));                     \
+      const float e2 = fast_ex2(fmaf(__uint_as_float(R[j + 2]), c, -mc));                     \
+      const float e3 = fast_ex2(fmaf(__uint_as_float(R[j + 3]), c, -mc));                     \
+      s0 += e0; s1 += e1; s2 += e2; s3 += e3;                                                 \
+      pk[j >> 1] = pack_bf16x2(e0, e1);                                                       \
+      pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);                                                 \
+    }                                                                                         \
+    tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
+  }
+        ci = 0;
+        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
+        for (; ci + 1 < nfull; ci += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
+          ATT_EXP32(ra, ci * 32)
+          tmem_ld_wait();
+          if (ci + 2 < nfull) tmem_ld_32x32b_x32(t_lane + (ci + 2) * 32, ra);
+          ATT_EXP32(rb, (ci + 1) * 32)
+        }
+        if (ci < nfull) {
+          tmem_ld_wait();
+          ATT_EXP32(ra, ci * 32)
+        }
+        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
+          uint32_t r16[16];
+          tmem_ld_32x32b_x16(t_lane + c0, r16);
+          tmem_ld_wait();
+          uint32_t pk8[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float e0 = (c0 + j < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[j]), c, -mc)) : 0.f;
+            const float e1 = (c0 + j + 1 < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[j + 1]), c, -mc)) : 0.f;
+            s0 += e0;
+            s1 += e1;
+            pk8[j >> 1] = pack_bf16x2(e0, e1);
           }
+          tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk8);
         }
-        if (PSMEM) {
-          fence_proxy_async_smem();
-        } else {
-          tmem_st_wait();
-        }
+#undef ATT_MAX32
+#undef ATT_EXP32
+        sum = (s0 + s1) + (s2 + s3);
+        tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
@@ -290,35 +270,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
+      uint32_t ob[32];  // 64 output columns as packed bf16 pairs
       if (warp_active) {
+        uint32_t r0[32];
         tmem_ld_32x32b_x32(t_lane + O_COL, r0);
-        tmem_ld_32x32b_x32(t_lane + O_COL + 32, r1);
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          ob[j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+        tmem_ld_32x32b_x32(t_lane + O_COL + 32, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          ob[16 + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
       if (warp_active && qrow < p.N) {
-        __nv_bfloat16* op = p.out + ((size_t)b * p.N + qrow) * p.I + h * ATT_DH;
+        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * ATT_DH);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(r0[j]) * inv, __uint_as_float(r0[j + 1]) * inv);
-          pk.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv, __uint_as_float(r0[j + 3]) * inv);
-          pk.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv, __uint_as_float(r0[j + 5]) * inv);
-          pk.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv, __uint_as_float(r0[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + j) = pk;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 pk;
-          pk.x = pack_bf16x2(__uint_as_float(r1[j]) * inv, __uint_as_float(r1[j + 1]) * inv);
-          pk.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv, __uint_as_float(r1[j + 3]) * inv);
-          pk.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv, __uint_as_float(r1[j + 5]) * inv);
-          pk.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv, __uint_as_float(r1[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + 32 + j) = pk;
-        }
+        for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
     }
   }
@@ -332,14 +304,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // debug / experiment knobs (b200vit_debug_set)
-static int g_attn_psmem = 0;     // 1: stage P through shared memory instead of TMEM
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 
-template <int NWG, int STAGES, bool PSMEM>
+template <int NWG, int STAGES>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, size_t smem_bytes,
                             cudaStream_t stream) {
-  auto kern = attention_kernel<NWG, STAGES, PSMEM>;
+  auto kern = attention_kernel<NWG, STAGES>;
   static size_t smem_set = 0;
   if (smem_bytes > smem_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -358,7 +329,7 @@ using namespace b200;
 
 extern "C" int b200vit_debug_set(int key, int value) {
   switch (key) {
-    case 1: g_attn_psmem = value; return 0;
+    case 1: return 0;  // (retired: P staging through shared memory)
     case 2: g_attn_v_lbo = value; return 0;
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
@@ -401,22 +372,18 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
     int rc = encode_tmap_bf16(&tmKV, qkv, 3, dims, strides, box);
     if (rc) return rc;
   }
-  const bool psmem = g_attn_psmem != 0;
   const size_t kv_bytes = (size_t)att_kv_bytes(p.kv_boxes, p.kv_box_rows);
   const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * 128 * 128;
-  const size_t p_bytes = psmem ? (size_t)nwg * ((p.KP + 63) / 64) * 128 * 128 : 0;
-  auto smem_for = [&](int st) { return st * stage_bytes + p_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
+  auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
   // two K/V/Q stages when they fit (prefetch of the next unit), else one
-  const int stages = (!psmem && smem_for(2) <= 227 * 1024) ? 2 : 1;
+  const int stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
   const size_t smem_bytes = smem_for(stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (nwg == 2) {
-    if (psmem) return launch_attention<2, 1, true>(tmQ, tmKV, p, smem_bytes, st);
-    if (stages == 1) return launch_attention<2, 1, false>(tmQ, tmKV, p, smem_bytes, st);
-    return launch_attention<2, 2, false>(tmQ, tmKV, p, smem_bytes, st);
+    if (stages == 1) return launch_attention<2, 1>(tmQ, tmKV, p, smem_bytes, st);
+    return launch_attention<2, 2>(tmQ, tmKV, p, smem_bytes, st);
   }
-  if (psmem) return launch_attention<1, 1, true>(tmQ, tmKV, p, smem_bytes, st);
-  if (stages == 1) return launch_attention<1, 1, false>(tmQ, tmKV, p, smem_bytes, st);
-  return launch_attention<1, 2, false>(tmQ, tmKV, p, smem_bytes, st);
+  if (stages == 1) return launch_attention<1, 1>(tmQ, tmKV, p, smem_bytes, st);
+  return launch_attention<1, 2>(tmQ, tmKV, p, smem_bytes, st);
 }

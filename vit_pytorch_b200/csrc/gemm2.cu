@@ -4,44 +4,46 @@
 //
 //   * each CTA of the pair owns 128 rows of A and HALF of the W tile (128 of the 256 N-rows); the pair's tensor cores
 //     run one 256 x 256 x 16 MMA (issued by the leader CTA) that reads both halves, so every SM stages only
-//     32 KB per 64-wide k-block (16 KB A + 16 KB W) instead of 48 KB  ->  5 stages + 64 KB of epilogue staging fit.
+//     32 KB per 64-wide k-block (16 KB A + 16 KB W) instead of 48 KB  ->  4-5 stages + 64-96 KB of epilogue staging.
 //   * accumulators: 2 x 256 fp32 columns of TMEM in each CTA (its own 128 rows), double buffered against the epilogue.
-//   * epilogue: 8 warps per CTA, thread == accumulator row (tcgen05.ld 32x32b), results written 16 B at a time into a
-//     128B-swizzled staging box (bank-conflict free) and shipped with TMA stores (fully coalesced, clipped at the
-//     matrix edges by the tensor map).  The fp32 residual stream is TMA-loaded into the same box, updated in place in
-//     shared memory and stored back, so no thread ever issues a strided global access.
+//   * epilogue: thread == accumulator row (tcgen05.ld 32x32b), results written 16 B at a time into 128B-swizzled
+//     staging boxes (bank-conflict free) and shipped with TMA stores (coalesced, clipped at the matrix edges).
+//       MODE_BF16 (QKV, FC1): 16 epilogue warps (4 per SM sub-partition: the GELU epilogue is latency/issue bound),
+//                             one 64-column bf16 box per warp per tile.
+//       MODE_F32  (patch, out-proj, FC2): 8 warps, 32-column fp32 boxes; the fp32 residual box is TMA-LOADED into the
+//                             staging buffer, updated in place in shared memory and stored back.
+//       MODE_DUAL (LN-fold producer): MODE_F32 + a bf16 copy of the new rows + their (sum, sum^2).
 //
 // Barrier protocol (every barrier exists at the same smem offset in both CTAs):
-//   full[s]      leader only : 1 arrive (leader producer, expect_tx = bytes of BOTH CTAs) + TMA complete_tx from both
-//   empty[s]     both        : tcgen05.commit multicast from the leader's MMA thread
-//   tmem_full[a] both        : tcgen05.commit multicast
-//   tmem_empty[a] leader only: 16 arrives = 8 epilogue warps x 2 CTAs (remote arrive from the peer)
+//   full[s]       leader only : 1 arrive (leader producer, expect_tx = bytes of BOTH CTAs) + TMA complete_tx from both
+//   empty[s]      both        : tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[a]  both        : tcgen05.commit multicast
+//   tmem_empty[a] leader only : 2 x EPI_WARPS arrives (remote arrive from the peer CTA's epilogue warps)
 #include "common.cuh"
 #include "host_util.h"
 
 namespace b200 {
 
 namespace g2 {
+constexpr int MODE_BF16 = 0, MODE_F32 = 1, MODE_DUAL = 2;
 constexpr int BLOCK_M = 128;       // rows per CTA (256 per pair)
 constexpr int BLOCK_N = 256;       // columns per tile (each CTA stages 128 W rows)
 constexpr int BLOCK_K = 64;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int EPI_BUF_BYTES = 4096;                   // one 32-row x 128-byte swizzled box
-constexpr int COLS_PER_WARP = BLOCK_N / 2;            // 128
-// DUAL (fp32 residual stream in place + bf16 copy + row statistics) needs a third staging box per warp, paid for
-// with one pipeline stage: 4 x 32 KB + 96 KB instead of 5 x 32 KB + 64 KB.
-template <bool DUAL>
+template <int MODE>
 struct Cfg {
-  static constexpr int STAGES = DUAL ? 4 : 5;
-  static constexpr int BUFS_PER_WARP = DUAL ? 3 : 2;
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * BUFS_PER_WARP * EPI_BUF_BYTES;
+  static constexpr int STAGES = MODE == MODE_DUAL ? 4 : 5;
+  static constexpr int EPI_WARPS = MODE == MODE_BF16 ? 16 : 8;
+  static constexpr int BUFS_PER_WARP = MODE == MODE_BF16 ? 1 : (MODE == MODE_DUAL ? 3 : 2);
+  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
+  static constexpr int EPI_BYTES = EPI_WARPS * BUFS_PER_WARP * EPI_BUF_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_BYTES;
-  // full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[8][2] + tmem ptr
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
+  // full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[EPI_WARPS][2] + tmem ptr
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS;
   static constexpr int DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 }  // namespace g2
@@ -50,32 +52,61 @@ struct Gemm2Params {
   int M, N, K;
   int num_m_pairs, num_n_tiles, num_k_blocks;
   int flags;
-  int out_is_f32;  // 0: bf16 output (tmOut is a bf16 map with 64-col boxes), 1: fp32 output (32-col boxes)
   const float* bias;
   const float* ln_sums;
   float ln_inv_dim, ln_eps;
   const float* col_s;
-  float* stats_out;  // DUAL: [M][2] (sum, sum of squares) of the bf16-rounded output rows, accumulated atomically
+  float* stats_out;  // MODE_DUAL: [M][2] (sum, sum of squares) of the bf16-rounded output rows (atomic)
 };
 
-template <bool DUAL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::NUM_THREADS, 1)
+// LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32)
+template <int W>
+__device__ __forceinline__ void epilogue_math(float (&v)[W], int col0, int flags, float mu, float rstd,
+                                              const Gemm2Params& p) {
+  if (flags & B200VIT_EPI_LNFOLD) {
+#pragma unroll
+    for (int j = 0; j < W; j += 4) {
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col0 + j < p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
+      v[j] = rstd * fmaf(-mu, s4.x, v[j]);
+      v[j + 1] = rstd * fmaf(-mu, s4.y, v[j + 1]);
+      v[j + 2] = rstd * fmaf(-mu, s4.z, v[j + 2]);
+      v[j + 3] = rstd * fmaf(-mu, s4.w, v[j + 3]);
+    }
+  }
+  if (flags & B200VIT_EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < W; j += 4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (flags & B200VIT_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+  }
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::Cfg<MODE>::NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmResid,
              const __grid_constant__ CUtensorMap tmOutB, const Gemm2Params p) {
   using namespace g2;
-  using C = Cfg<DUAL>;
+  using C = Cfg<MODE>;
   constexpr int STAGES = C::STAGES;
-  constexpr int BAR_OFFSET = C::BAR_OFFSET;
+  constexpr int EPI_WARPS = C::EPI_WARPS;
+  constexpr int COLS_PER_WARP = C::COLS_PER_WARP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* resid_full = tmem_empty + 2;  // [NUM_EPI_WARPS][2]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(resid_full + 2 * NUM_EPI_WARPS);
+  uint64_t* resid_full = tmem_empty + 2;  // [EPI_WARPS][2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(resid_full + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,6 +118,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     if (p.flags & B200VIT_EPI_RESIDUAL) tma_prefetch_desc(&tmResid);
+    if (MODE == MODE_DUAL) tma_prefetch_desc(&tmOutB);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -95,9 +127,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
     }
-    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(&resid_full[i], 1);
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resid_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -178,103 +210,138 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int quad = warp & 3;
     const int col_off = (e >> 2) * COLS_PER_WARP;
     const int flags = p.flags;
-    const bool has_resid = (flags & B200VIT_EPI_RESIDUAL) != 0;
-    uint8_t* buf0 = epi_smem + e * C::BUFS_PER_WARP * EPI_BUF_BYTES;
-    uint8_t* bbuf = buf0 + 2 * EPI_BUF_BYTES;  // DUAL only: bf16 copy staging box (64 columns)
-    float st_sum = 0.f, st_sq = 0.f;
-    uint64_t* rbar = resid_full + 2 * e;
     const uint32_t tmem_empty_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    uint8_t* buf0 = epi_smem + e * C::BUFS_PER_WARP * EPI_BUF_BYTES;
     uint8_t* my_row0 = buf0 + lane * 128;  // this thread's 128-byte row inside a staging box
-
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t box_seq = 0;  // running count of staging boxes used by this warp (buffer = box_seq & 1)
 
-    // fp32 mode: 4 boxes of 32 columns per tile;  bf16 mode: 2 boxes of 64 columns per tile
-    const int boxes_per_tile = p.out_is_f32 ? 4 : 2;
-
-    auto box_coords = [&](int tile, int box, int& c_col, int& c_row) {
-      const int m_pair = tile / p.num_n_tiles;
-      const int n_blk = tile % p.num_n_tiles;
-      c_row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
-      c_col = n_blk * BLOCK_N + col_off + box * (p.out_is_f32 ? 32 : 64);
-    };
-    // residual prefetch of box `seq` (global stream order over this CTA's tiles) into buffer seq & 1
-    auto prefetch_resid = [&](int tile, int box, uint32_t seq) {
-      if (lane == 0) {
-        int cc, cr;
-        box_coords(tile, box, cc, cr);
-        tma_store_wait_read<0>();  // the store that last used this buffer has finished reading it
-        mbar_arrive_expect_tx(&rbar[seq & 1], EPI_BUF_BYTES);
-        tma_load_2d(buf0 + (seq & 1) * EPI_BUF_BYTES, &tmResid, &rbar[seq & 1], cc, cr);
-      }
+    auto release_tmem = [&]() {
+      // all TMEM reads of this tile are done: hand the accumulator back to the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
     };
 
-    int first_tile = cluster_id;
-    if (has_resid && first_tile < num_tiles) {
-      prefetch_resid(first_tile, 0, 0);
-      prefetch_resid(first_tile, 1, 1);
-    }
+    if constexpr (MODE == MODE_BF16) {
+      // ============ bf16 output: 64 columns per warp = one staging box per tile, x16 loads double buffered
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_pair = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        const int row0 = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
+        const int row = row0 + lane;
+        float mu = 0.f, rstd = 1.f;
+        if ((flags & B200VIT_EPI_LNFOLD) && row < p.M) {
+          const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
+          mu = ss.x * p.ln_inv_dim;
+          rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+        }
+        const int col_base = n_blk * BLOCK_N + col_off;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x32b_x16(t_row, ra);
+        if (lane == 0) tma_store_wait_read<0>();  // last tile's store has finished reading the staging box
+        __syncwarp();
 
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_pair = tile / p.num_n_tiles;
-      const int n_blk = tile % p.num_n_tiles;
-      const int row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      float mu = 0.f, rstd = 1.f;
-      if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
-        const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
-        mu = ss.x * p.ln_inv_dim;
-        rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+        auto emit16 = [&](const uint32_t (&r)[16], int cidx) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_math<16>(v, col_base + cidx * 16, flags, mu, rstd, p);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
+            pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+            pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(my_row0 + ((static_cast<uint32_t>(cidx * 2 + q) ^ sw) << 4)) = pk;
+          }
+        };
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(t_row + 16, rb);
+        emit16(ra, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(t_row + 32, ra);
+        emit16(rb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(t_row + 48, rb);
+        emit16(ra, 2);
+        tmem_ld_wait();
+        release_tmem();
+        emit16(rb, 3);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, buf0, col_base, row0);
+          tma_store_commit();
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
-      if (DUAL) st_sum = st_sq = 0.f;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
+    } else {
+      // ============ fp32 output (optionally residual in place, optionally + bf16 copy + statistics)
+      constexpr bool DUAL = MODE == MODE_DUAL;
+      const bool has_resid = (flags & B200VIT_EPI_RESIDUAL) != 0;
+      uint8_t* bbuf = buf0 + 2 * EPI_BUF_BYTES;  // DUAL only: bf16 copy staging box (64 columns)
+      uint64_t* rbar = resid_full + 2 * e;
+      uint32_t box_seq = 0;  // running count of fp32 boxes used by this warp (buffer = box_seq & 1)
+      float st_sum = 0.f, st_sq = 0.f;
+
+      auto box_coords = [&](int tile, int box, int& c_col, int& c_row) {
+        const int m_pair = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        c_row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
+        c_col = n_blk * BLOCK_N + col_off + box * 32;
+      };
+      // residual prefetch of box `seq` (stream order over this CTA's tiles) into buffer seq & 1
+      auto prefetch_resid = [&](int tile, int box, uint32_t seq) {
+        if (lane == 0) {
+          int cc, cr;
+          box_coords(tile, box, cc, cr);
+          tma_store_wait_read<0>();  // the store that last used this buffer has finished reading it
+          mbar_arrive_expect_tx(&rbar[seq & 1], EPI_BUF_BYTES);
+          tma_load_2d(buf0 + (seq & 1) * EPI_BUF_BYTES, &tmResid, &rbar[seq & 1], cc, cr);
+        }
+      };
+      if (has_resid && cluster_id < num_tiles) {
+        prefetch_resid(cluster_id, 0, 0);
+        prefetch_resid(cluster_id, 1, 1);
+      }
+
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_pair = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        const int row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32 + lane;
+        const bool row_ok = row < p.M;
+        float mu = 0.f, rstd = 1.f;
+        if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
+          const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
+          mu = ss.x * p.ln_inv_dim;
+          rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+        }
+        if (DUAL) st_sum = st_sq = 0.f;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
 
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
-        tmem_ld_wait();
-        if (c + 32 == COLS_PER_WARP) {
-          // all TMEM reads of this tile are done: hand the accumulator back to the leader's MMA thread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-        }
-        const int col0 = n_blk * BLOCK_N + col_off + c;
-        float v[32];
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_wait();
+          if (c + 32 == COLS_PER_WARP) release_tmem();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (flags & B200VIT_EPI_LNFOLD) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + j < p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
-            v[j] = rstd * fmaf(-mu, s4.x, v[j]);
-            v[j + 1] = rstd * fmaf(-mu, s4.y, v[j + 1]);
-            v[j + 2] = rstd * fmaf(-mu, s4.z, v[j + 2]);
-            v[j + 3] = rstd * fmaf(-mu, s4.w, v[j + 3]);
-          }
-        }
-        if (flags & B200VIT_EPI_BIAS) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if (flags & B200VIT_EPI_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_math<32>(v, n_blk * BLOCK_N + col_off + c, flags, mu, rstd, p);
 
-        if (p.out_is_f32) {
-          // ---- one 32-column fp32 box per chunk
           uint8_t* myrow = my_row0 + (box_seq & 1) * EPI_BUF_BYTES;
           if (has_resid) {
             mbar_wait(&rbar[box_seq & 1], (box_seq >> 1) & 1);
@@ -330,54 +397,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (has_resid) {
             // prefetch the residual box that will use this buffer next (two boxes ahead in stream order)
             int nbox = (c >> 5) + 2, ntile = tile;
-            if (nbox >= 4) {
-              nbox -= 4;
+            if (nbox >= COLS_PER_WARP / 32) {
+              nbox -= COLS_PER_WARP / 32;
               ntile += num_clusters;
             }
             if (ntile < num_tiles) prefetch_resid(ntile, nbox, box_seq + 2);
           }
           ++box_seq;
-        } else {
-          // ---- bf16: two 32-column chunks fill one 64-column box
-          const int half = (c >> 5) & 1;
-          uint8_t* myrow = my_row0 + (box_seq & 1) * EPI_BUF_BYTES;
-          if (half == 0) {
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
-            pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-            pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-            pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-            *reinterpret_cast<uint4*>(myrow + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4)) = pk;
-          }
-          if (half == 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              int cc, cr;
-              box_coords(tile, c >> 6, cc, cr);
-              tma_store_2d(&tmOut, buf0 + (box_seq & 1) * EPI_BUF_BYTES, cc, cr);
-              tma_store_commit();
-            }
-            ++box_seq;
-          }
+        }
+        if (DUAL && row_ok) {
+          atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
+          atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
       }
-      if (DUAL && row_ok) {
-        atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
-        atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
     }
-    (void)boxes_per_tile;
-    if (lane == 0) tma_store_wait<0>();  // all global writes of this warp issued and complete before exit
+    if (lane == 0) tma_store_wait<0>();  // all global writes of this warp complete before exit
   }
 
   // ------------------------------------------------------------------ teardown
@@ -389,11 +427,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-static int g_gemm_force = 0;  // debug: 0 auto, 1 force v1, 2 force v2 (error if ineligible)
+static int g_gemm_force = 0;  // debug: 0 auto, 1 force v1, 2 force v2 (wherever its epilogue applies)
 
 int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_bf16, const float* out_f32,
                    const float* resid) {
   (void)K;
+  (void)resid;
   if (g_gemm_force == 1) return 0;
   const bool dual = out_bf16 && out_f32;
   if (dual) {
@@ -402,29 +441,28 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
     if ((ldo % 8) != 0 || (N % 64) != 0) return 0;
   } else {
     if (flags & B200VIT_EPI_STATS) return 0;
+    if (out_bf16 && (flags & B200VIT_EPI_RESIDUAL)) return 0;
+    if (out_f32 && (flags & B200VIT_EPI_GELU)) return 0;
   }
-  if (!dual && out_bf16 && (flags & B200VIT_EPI_RESIDUAL)) return 0;
-  if (out_f32 && (flags & B200VIT_EPI_GELU)) return 0;
-  if (out_bf16 && (ldo % 8) != 0) return 0;                // TMA: 16-byte row pitch
+  if (out_bf16 && (ldo % 8) != 0) return 0;  // TMA: 16-byte row pitch
   if (out_f32 && (ldo % 4) != 0) return 0;
-  if ((N % 4) != 0) return 0;                              // float4 bias / col_s loads
-  if (resid && resid != out_f32 && false) return 0;
+  if ((N % 4) != 0) return 0;                // float4 bias / col_s loads
   if (g_gemm_force == 2) return 1;
-  return (M >= 1024 && N >= 256) ? 1 : 0;                  // small problems: the single-CTA kernel has finer tiles
+  return (M >= 1024 && N >= 256) ? 1 : 0;    // small problems: the single-CTA kernel has finer tiles
 }
 
-template <bool DUAL>
+template <int MODE>
 static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmResid, const CUtensorMap& tmOutB, const Gemm2Params& p, int clusters,
                           cudaStream_t stream) {
-  using namespace g2;
-  auto kern = gemm2_kernel<DUAL>;
+  using C = g2::Cfg<MODE>;
+  auto kern = gemm2_kernel<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<DUAL>::DYN_BYTES));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
     attr_set = true;
   }
-  kern<<<2 * clusters, NUM_THREADS, Cfg<DUAL>::DYN_BYTES, stream>>>(tmA, tmB, tmOut, tmResid, tmOutB, p);
+  kern<<<2 * clusters, C::NUM_THREADS, C::DYN_BYTES, stream>>>(tmA, tmB, tmOut, tmResid, tmOutB, p);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -442,7 +480,6 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.flags = flags;
-  p.out_is_f32 = out_f32 ? 1 : 0;
   p.bias = bias;
   p.ln_sums = ln_sums;
   p.ln_inv_dim = 1.0f / (float)K;
@@ -464,26 +501,25 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
+  const uint64_t odims[2] = {(uint64_t)N, (uint64_t)M};
   if (out_f32) {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)ldo * 4};
     const uint32_t box[2] = {32, 32};
-    int rc = encode_tmap_f32(&tmOut, out_f32, 2, dims, strides, box, true);
+    int rc = encode_tmap_f32(&tmOut, out_f32, 2, odims, strides, box, true);
     if (rc) return rc;
-    rc = encode_tmap_f32(&tmResid, resid ? resid : out_f32, 2, dims, strides, box, true);
+    rc = encode_tmap_f32(&tmResid, resid ? resid : out_f32, 2, odims, strides, box, true);
     if (rc) return rc;
     tmOutB = tmOut;
     if (dual) {
       const uint64_t bstrides[1] = {(uint64_t)ldo * 2};
       const uint32_t bbox[2] = {64, 32};
-      rc = encode_tmap_bf16(&tmOutB, out_bf16, 2, dims, bstrides, bbox);
+      rc = encode_tmap_bf16(&tmOutB, out_bf16, 2, odims, bstrides, bbox);
       if (rc) return rc;
     }
   } else {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)ldo * 2};
     const uint32_t box[2] = {64, 32};
-    int rc = encode_tmap_bf16(&tmOut, out_bf16, 2, dims, strides, box);
+    int rc = encode_tmap_bf16(&tmOut, out_bf16, 2, odims, strides, box);
     if (rc) return rc;
     tmResid = tmOut;
     tmOutB = tmOut;
@@ -493,9 +529,10 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   if (tiles < clusters) clusters = tiles;
   if (dual) {
     B200_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * sizeof(float), stream));
-    return launch_gemm2_t<true>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+    return launch_gemm2_t<MODE_DUAL>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
   }
-  return launch_gemm2_t<false>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+  if (out_f32) return launch_gemm2_t<MODE_F32>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+  return launch_gemm2_t<MODE_BF16>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
 }
 
 void gemm_force_version(int v) { g_gemm_force = v; }
