@@ -211,14 +211,17 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- end to end through the public API with host buffers (H2D of the batch + D2H of the logits every step) ----
+    from vit_pytorch_b200.io import DeviceFeeder
     host_img = torch.empty(B, 3, 224, 224, dtype=torch.bfloat16).pin_memory()
     host_img.copy_(img)
     host_out = torch.empty(world * B, VIT_B16["num_classes"], dtype=torch.bfloat16).pin_memory()
-    dev_img = torch.empty_like(img)
+    feeder = DeviceFeeder(tuple(img.shape), torch.bfloat16, dev)
 
     def e2e_step():
-        dev_img.copy_(host_img, non_blocking=True)
-        o = step(dev_img)
+        # every step copies its own batch host -> device (the copy of step i+1 overlaps the forward of step i)
+        x = feeder.push(host_img, next_host=host_img)
+        o = step(x)
+        feeder.done(x)
         host_out.copy_(o, non_blocking=True)
 
     for _ in range(3):

@@ -32,7 +32,7 @@ extern "C" {
 #define B200VIT_EPI_GELU 2      /* exact-erf GELU (nn.GELU default, vit.py:21) */
 #define B200VIT_EPI_RESIDUAL 4  /* + resid[m, n] (fp32); resid may alias out_f32 (in-place residual stream) */
 #define B200VIT_EPI_LNFOLD 8    /* A is the un-normalised bf16 row, W carries gamma: y = rstd_m*(acc - mu_m*s_n) + bias_n */
-#define B200VIT_EPI_STATS 16    /* atomically accumulate per-row (sum, sum^2) of the bf16-rounded result into stats_out */
+#define B200VIT_EPI_STATS 16    /* write per-row partial (sum, sum^2) of the bf16-rounded result into stats_out */
 
 const char* b200vit_last_error(void);
 int b200vit_version(void);
@@ -48,13 +48,17 @@ int b200vit_device_ok(int dev);
  *   vit.py:20,23 (FeedForward), vit.py:44,47 (to_qkv / to_out), vit.py:102 (patch projection), vit.py:116 (mlp_head);
  *   simple_vit.py:30,32,47,48,93,108.
  * out_bf16 and/or out_f32 (either may be NULL, not both), row stride ldo (elements).
- * EPI_LNFOLD: ln_sums[M][2] = per-row (sum, sum of squares) of A, ln_dim = K, col_s[N] = sum_k W[n,k] (fp32).
- * EPI_STATS:  stats_out[M][2] is zeroed by the call, then receives (sum, sum of squares) of the bf16-rounded rows.
+ * EPI_LNFOLD: ln_sums[M][ln_parts][2] = per-row PARTIAL (sum, sum of squares) of A (added up in index order, so the
+ *             result is deterministic), ln_dim = K, col_s[N] = sum_k W[n,k] (fp32).
+ * EPI_STATS:  stats_out[M][P][2], P = b200vit_stats_parts(N): every slot is written exactly once (no atomics).
  * Requirements: A, W 16-byte aligned, lda, ldw multiples of 8, K multiple of 8.
  */
 int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32,
-                      int64_t ldo, const float* bias, const float* resid, const float* ln_sums, float ln_eps,
-                      const float* col_s, float* stats_out, int M, int N, int K, int flags, void* stream);
+                      int64_t ldo, const float* bias, const float* resid, const float* ln_sums, int ln_parts,
+                      float ln_eps, const float* col_s, float* stats_out, int M, int N, int K, int flags,
+                      void* stream);
+/* number of per-row partial statistics an EPI_STATS GEMM with N output columns writes */
+int b200vit_stats_parts(int N);
 
 /*
  * LayerNorm over the last dim of an fp32 [M, D] matrix (row stride ldx) -> bf16 and/or fp32 outputs.

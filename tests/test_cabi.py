@@ -33,12 +33,13 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_launch_counter(lib):
     assert lib.b200vit_version() >= 100
+    assert lib.b200vit_stats_parts(768) == 6 and lib.b200vit_stats_parts(128) == 2 and lib.b200vit_stats_parts(1000) == 8
     lib.b200vit_reset_launch_count()
     assert lib.b200vit_launch_count() == 0
 
 
 def test_bad_arguments_return_error_codes(lib):
-    rc = lib.b200vit_gemm_bf16(None, 8, None, 8, None, None, 8, None, None, None, 1e-5, None, None, 1, 1, 8, 0, None)
+    rc = lib.b200vit_gemm_bf16(None, 8, None, 8, None, None, 8, None, None, None, 0, 1e-5, None, None, 1, 1, 8, 0, None)
     assert rc == -1 and b"null" in lib.b200vit_last_error()
     rc = lib.b200vit_attention(ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 16, 1, 80, 0.1, None)
     assert rc == -1 and b"dim_head=80" in lib.b200vit_last_error()

@@ -78,10 +78,13 @@ def test_gemm_lnfold_and_stats():
     af = a.float()
     sums = torch.stack([af.sum(1), (af * af).sum(1)], 1).contiguous()
     out = torch.zeros(M, N, device=DEV)
-    st = torch.zeros(M, 2, device=DEV)
+    st = torch.full((M, _lib.stats_parts(N), 2), 9.0, device=DEV)     # every slot must be overwritten
     ob = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    _lib.gemm(a, wg, out_f32=out, out_bf16=ob, bias=t.contiguous(), ln_sums=sums, col_s=col_s.contiguous(),
+    # partial input statistics in two unequal parts: the kernel adds them up in order
+    sums2 = torch.stack([sums * 0.25, sums * 0.75], 1).contiguous()
+    _lib.gemm(a, wg, out_f32=out, out_bf16=ob, bias=t.contiguous(), ln_sums=sums2, col_s=col_s.contiguous(),
               stats_out=st)
+    st = st.sum(1)
     # (a) the kernel's arithmetic, against the same folded formula evaluated in fp32 on the host
     mu = af.mean(1, keepdim=True)
     rstd = torch.rsqrt((af * af).mean(1, keepdim=True) - mu * mu + 1e-5)
@@ -142,8 +145,9 @@ def test_embed_tokens(ncls):
     pos = torch.randn(n + ncls, D, device=DEV)
     x = torch.zeros(B * (n + ncls), D, device=DEV)
     xb = torch.zeros(B * (n + ncls), D, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(B * (n + ncls), 2, device=DEV)
+    st = torch.zeros(B * (n + ncls), 1, 2, device=DEV)
     _lib.embed_tokens(y, g, be, cls, pos, x, B, n, ncls, xb=xb, stats=st)
+    st = st[:, 0]
     t = O.layer_norm(y.cpu(), g.cpu(), be.cpu()).view(B, n, D)
     if ncls:
         t = torch.cat([cls.cpu()[None].expand(B, -1, -1), t], 1)
@@ -159,8 +163,9 @@ def test_rowstats_cast():
     torch.manual_seed(8)
     x = torch.randn(333, 768, device=DEV) * 2 + 0.5
     xb = torch.zeros(333, 768, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(333, 2, device=DEV)
+    st = torch.zeros(333, 1, 2, device=DEV)
     _lib.rowstats_cast(x, xb, st)
+    st = st[:, 0]
     assert torch.equal(xb, x.bfloat16())
     xr = xb.float()
     assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-5, atol=1e-3)
@@ -177,8 +182,13 @@ def test_gemm_pair_kernel_dual_epilogue(M, N, K):
     x0 = torch.randn(M, N, device=DEV)
     x = x0.clone()
     xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    st = torch.full((M, 2), 123.0, device=DEV)          # the call must zero it
+    st = torch.full((M, _lib.stats_parts(N), 2), 123.0, device=DEV)          # every slot must be overwritten
     _lib.gemm(a, w, out_f32=x, out_bf16=xb, bias=b, resid=x, stats_out=st)
+    st2 = st.clone()
+    x2 = x0.clone()
+    _lib.gemm(a, w, out_f32=x2, out_bf16=xb, bias=b, resid=x2, stats_out=st2)
+    assert torch.equal(st, st2) and torch.equal(x, x2)                        # deterministic, no atomics
+    st = st.sum(1)
     ref = O.linear(a.float().cpu(), w.float().cpu(), b.cpu()) + x0.cpu()
     assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
     assert torch.equal(xb, x.bfloat16())
@@ -248,8 +258,9 @@ def test_embed_tokens(ncls):
     pos = torch.randn(n + ncls, D, device=DEV)
     x = torch.zeros(B * (n + ncls), D, device=DEV)
     xb = torch.zeros(B * (n + ncls), D, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(B * (n + ncls), 2, device=DEV)
+    st = torch.zeros(B * (n + ncls), 1, 2, device=DEV)
     _lib.embed_tokens(y, g, be, cls, pos, x, B, n, ncls, xb=xb, stats=st)
+    st = st[:, 0]
     t = O.layer_norm(y.cpu(), g.cpu(), be.cpu()).view(B, n, D)
     if ncls:
         t = torch.cat([cls.cpu()[None].expand(B, -1, -1), t], 1)
@@ -265,8 +276,9 @@ def test_rowstats_cast():
     torch.manual_seed(8)
     x = torch.randn(333, 768, device=DEV) * 2 + 0.5
     xb = torch.zeros(333, 768, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(333, 2, device=DEV)
+    st = torch.zeros(333, 1, 2, device=DEV)
     _lib.rowstats_cast(x, xb, st)
+    st = st[:, 0]
     assert torch.equal(xb, x.bfloat16())
     xr = xb.float()
     assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-5, atol=1e-3)
@@ -283,8 +295,13 @@ def test_gemm_pair_kernel_dual_epilogue(M, N, K):
     x0 = torch.randn(M, N, device=DEV)
     x = x0.clone()
     xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    st = torch.full((M, 2), 123.0, device=DEV)          # the call must zero it
+    st = torch.full((M, _lib.stats_parts(N), 2), 123.0, device=DEV)          # every slot must be overwritten
     _lib.gemm(a, w, out_f32=x, out_bf16=xb, bias=b, resid=x, stats_out=st)
+    st2 = st.clone()
+    x2 = x0.clone()
+    _lib.gemm(a, w, out_f32=x2, out_bf16=xb, bias=b, resid=x2, stats_out=st2)
+    assert torch.equal(st, st2) and torch.equal(x, x2)                        # deterministic, no atomics
+    st = st.sum(1)
     ref = O.linear(a.float().cpu(), w.float().cpu(), b.cpu()) + x0.cpu()
     assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
     assert torch.equal(xb, x.bfloat16())

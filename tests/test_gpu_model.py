@@ -126,7 +126,13 @@ def test_vit_b16_against_oracle(kind):
     assert mx < 0.0211 and frac > (0.90 if kind == "vit" else 0.928), (mx, mean, frac)
 
 
-def test_full_batch_properties_b512():
+@pytest.mark.parametrize("mode", ["exact", "fold"])
+def test_full_batch_properties_b512(mode, monkeypatch):
+    monkeypatch.setenv("B200VIT_LN_MODE", mode)
+    _full_batch_properties_b512()
+
+
+def _full_batch_properties_b512():
     """BASELINE.json configs[1] at its full batch (512): properties that need no oracle run --
     (1) batch-permutation equivariance, bit exact (every image is computed independently of its batch slot);
     (2) batch-size invariance: image i gives the same logits in a batch of 512 and in a batch of 2;

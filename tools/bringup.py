@@ -64,7 +64,7 @@ def case_gemm(M, N, K, bias=False, gelu=False, resid=False, f32=False, both=Fals
         ref = torch.nn.functional.gelu(ref)
     if resid:
         ref = ref + r
-    st = torch.zeros(M, 2, device=dev) if stats else None
+    st = torch.zeros(M, _lib.stats_parts(N), 2, device=dev) if stats else None
     if inplace:
         out_f32 = r.clone()
         _lib.gemm(a, w, out_f32=out_f32, bias=b, resid=out_f32)
@@ -83,8 +83,8 @@ def case_gemm(M, N, K, bias=False, gelu=False, resid=False, f32=False, both=Fals
         res["f32"] = _err(out_f32_first if inplace else out_f32, ref)
     if stats:
         rb = ref.bfloat16().float()
-        res["stats_sum"] = _err(st[:, 0], rb.sum(1))
-        res["stats_sq"] = _err(st[:, 1], (rb * rb).sum(1))
+        res["stats_sum"] = _err(st.sum(1)[:, 0], rb.sum(1))
+        res["stats_sq"] = _err(st.sum(1)[:, 1], (rb * rb).sum(1))
     # timing
     if M * N * K > 1e9:
         r = r_arg

@@ -26,6 +26,7 @@ SYMBOLS = [
     "b200vit_last_error", "b200vit_version", "b200vit_launch_count", "b200vit_reset_launch_count",
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
+    "b200vit_stats_parts",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -54,7 +55,10 @@ def lib() -> C.CDLL:
     L.b200vit_device_ok.restype = i32
     L.b200vit_device_ok.argtypes = [i32]
     L.b200vit_gemm_bf16.restype = i32
-    L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp]
+    L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
+                                    vp]
+    L.b200vit_stats_parts.restype = i32
+    L.b200vit_stats_parts.argtypes = [i32]
     L.b200vit_layernorm.restype = i32
     L.b200vit_layernorm.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, f32, vp]
     L.b200vit_patchify_ln.restype = i32
@@ -150,7 +154,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
          resid: Optional[torch.Tensor] = None, gelu: bool = False, ln_sums: Optional[torch.Tensor] = None,
          ln_eps: float = 1e-5, col_s: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
          n: Optional[int] = None, k: Optional[int] = None) -> None:
-    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last stride 1)."""
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last stride 1).
+
+    ln_sums: [M, parts, 2] (or [M, 2]) partial row sums of `a`; stats_out: [M, stats_parts(N), 2], fully overwritten."""
     _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
     _chk(out_bf16, torch.bfloat16, "out_bf16"); _chk(out_f32, torch.float32, "out_f32")
     for nm, t in (("bias", bias), ("resid", resid), ("ln_sums", ln_sums), ("col_s", col_s), ("stats_out", stats_out)):
@@ -171,15 +177,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
     if resid is not None:
         flags |= EPI_RESIDUAL
         assert resid.stride(0) == out.stride(0)
+    ln_parts = 0
     if ln_sums is not None:
         flags |= EPI_LNFOLD
+        assert ln_sums.is_contiguous() and ln_sums.shape[0] == M and ln_sums.shape[-1] == 2
+        ln_parts = 1 if ln_sums.dim() == 2 else ln_sums.shape[1]
     if stats_out is not None:
         flags |= EPI_STATS
+        assert stats_out.is_contiguous() and tuple(stats_out.shape) == (M, stats_parts(N), 2), \
+            f"stats_out must be [M, {stats_parts(N)}, 2]"
     with _Timed("gemm", M=M, N=N, K=K, flags=flags, flops=2.0 * M * N * K):
         rc = lib().b200vit_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
-                                     out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), float(ln_eps),
+                                     out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), ln_parts, float(ln_eps),
                                      _ptr(col_s), _ptr(stats_out), M, N, K, flags, _stream())
     _check(rc, "b200vit_gemm_bf16")
+
+
+def stats_parts(n: int) -> int:
+    return int(lib().b200vit_stats_parts(int(n)))
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor], *,

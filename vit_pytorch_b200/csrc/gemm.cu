@@ -28,7 +28,9 @@ struct GemmParams {
   long long ldo;
   const float* bias;
   const float* resid;
-  const float* ln_sums;  // [M][2]
+  const float* ln_sums;  // [M][ln_parts][2]
+  int ln_parts;
+  int stats_parts;
   float ln_inv_dim;
   float ln_eps;
   const float* col_s;  // [N]
@@ -167,9 +169,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       float mu = 0.f, rstd = 1.f;
       if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
-        const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
-        mu = ss.x * p.ln_inv_dim;
-        const float var = fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
+          s1 += ss.x;
+          s2 += ss.y;
+        }
+        mu = s1 * p.ln_inv_dim;
+        const float var = fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f);
         rstd = rsqrtf(var + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;
@@ -265,8 +272,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if ((flags & B200VIT_EPI_STATS) && row_ok) {
-        atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
-        atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
+        const int part = n_blk * (NUM_EPI_WARPS / 4) + (e >> 2);
+        *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part)) =
+            make_float2(st_sum, st_sq);
       }
       if (++acc == 2) {
         acc = 0;
@@ -306,10 +314,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 
 }  // namespace b200
 
+extern "C" int b200vit_stats_parts(int N) {
+  const int block_n = N > 128 ? 256 : 128;      // both GEMM kernels: two column halves per N tile
+  return 2 * ((N + block_n - 1) / block_n);
+}
+
 extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16,
                                  float* out_f32, int64_t ldo, const float* bias, const float* resid,
-                                 const float* ln_sums, float ln_eps, const float* col_s, float* stats_out, int M, int N,
-                                 int K, int flags, void* stream) {
+                                 const float* ln_sums, int ln_parts, float ln_eps, const float* col_s,
+                                 float* stats_out, int M, int N, int K, int flags, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(A && W, "gemm: A/W must not be null");
   B200_CHECK_ARG(out_bf16 || out_f32, "gemm: need at least one output");
@@ -321,7 +334,8 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   B200_CHECK_ARG(ldo >= N, "gemm: ldo=%lld < N=%d", (long long)ldo, N);
   B200_CHECK_ARG(!(flags & B200VIT_EPI_BIAS) || bias, "gemm: EPI_BIAS without bias");
   B200_CHECK_ARG(!(flags & B200VIT_EPI_RESIDUAL) || resid, "gemm: EPI_RESIDUAL without resid");
-  B200_CHECK_ARG(!(flags & B200VIT_EPI_LNFOLD) || (ln_sums && col_s), "gemm: EPI_LNFOLD without ln_sums/col_s");
+  B200_CHECK_ARG(!(flags & B200VIT_EPI_LNFOLD) || (ln_sums && col_s && ln_parts >= 1 && ln_parts <= 64),
+                 "gemm: EPI_LNFOLD needs ln_sums, col_s and 1 <= ln_parts <= 64");
   B200_CHECK_ARG(!(flags & B200VIT_EPI_STATS) || stats_out, "gemm: EPI_STATS without stats_out");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   B200_CHECK_ARG(al16(bias) && al16(resid) && al16(col_s) && al16(out_bf16) && al16(out_f32) && al16(ln_sums),
@@ -329,8 +343,8 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (gemm2_eligible(M, N, K, ldo, flags, out_bf16, out_f32, resid))
-    return launch_gemm2(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_eps, col_s, stats_out, M, N,
-                        K, flags, st);
+    return launch_gemm2(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_parts, ln_eps, col_s,
+                        stats_out, M, N, K, flags, st);
 
   // K-tail: TMA zero-fills out-of-bounds columns of both operands, so any K works as long as rows are 16B multiples.
   GemmParams p{};
@@ -342,6 +356,8 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.bias = bias;
   p.resid = resid;
   p.ln_sums = ln_sums;
+  p.ln_parts = ln_parts;
+  p.stats_parts = b200vit_stats_parts(N);
   p.ln_inv_dim = 1.0f / (float)K;
   p.ln_eps = ln_eps;
   p.col_s = col_s;
@@ -364,7 +380,6 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  if (flags & B200VIT_EPI_STATS) B200_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * sizeof(float), st));
   if (wide) return launch_gemm<256, 4>(tmA, tmB, p, st);
   return launch_gemm<128, 6>(tmA, tmB, p, st);
 }

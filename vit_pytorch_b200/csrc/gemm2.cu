@@ -53,10 +53,12 @@ struct Gemm2Params {
   int num_m_pairs, num_n_tiles, num_k_blocks;
   int flags;
   const float* bias;
-  const float* ln_sums;
+  const float* ln_sums;  // [M][ln_parts][2]
+  int ln_parts;
+  int stats_parts;
   float ln_inv_dim, ln_eps;
   const float* col_s;
-  float* stats_out;  // MODE_DUAL: [M][2] (sum, sum of squares) of the bf16-rounded output rows (atomic)
+  float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
 };
 
 // LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32)
@@ -234,9 +236,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row = row0 + lane;
         float mu = 0.f, rstd = 1.f;
         if ((flags & B200VIT_EPI_LNFOLD) && row < p.M) {
-          const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
-          mu = ss.x * p.ln_inv_dim;
-          rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
+            s1 += ss.x;
+            s2 += ss.y;
+          }
+          mu = s1 * p.ln_inv_dim;
+          rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
         }
         const int col_base = n_blk * BLOCK_N + col_off;
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -322,9 +329,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool row_ok = row < p.M;
         float mu = 0.f, rstd = 1.f;
         if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
-          const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * (size_t)row);
-          mu = ss.x * p.ln_inv_dim;
-          rstd = rsqrtf(fmaxf(ss.y * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
+            s1 += ss.x;
+            s2 += ss.y;
+          }
+          mu = s1 * p.ln_inv_dim;
+          rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
         }
         if (DUAL) st_sum = st_sq = 0.f;
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -406,8 +418,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ++box_seq;
         }
         if (DUAL && row_ok) {
-          atomicAdd(p.stats_out + 2 * (size_t)row, st_sum);
-          atomicAdd(p.stats_out + 2 * (size_t)row + 1, st_sq);
+          const int part = n_blk * 2 + (e >> 2);
+          *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part)) =
+              make_float2(st_sum, st_sq);
         }
         if (++acc == 2) {
           acc = 0;
@@ -469,8 +482,8 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
-                 const float* bias, const float* resid, const float* ln_sums, float ln_eps, const float* col_s,
-                 float* stats_out, int M, int N, int K, int flags, cudaStream_t stream) {
+                 const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
+                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream) {
   using namespace g2;
   const bool dual = out_bf16 && out_f32;
   Gemm2Params p{};
@@ -482,6 +495,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.flags = flags;
   p.bias = bias;
   p.ln_sums = ln_sums;
+  p.ln_parts = ln_parts;
+  p.stats_parts = b200vit_stats_parts(N);
   p.ln_inv_dim = 1.0f / (float)K;
   p.ln_eps = ln_eps;
   p.col_s = col_s;
@@ -528,7 +543,6 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
   if (dual) {
-    B200_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * sizeof(float), stream));
     return launch_gemm2_t<MODE_DUAL>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
   }
   if (out_f32) return launch_gemm2_t<MODE_F32>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);

@@ -43,8 +43,8 @@ int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_bf16, const float* out_f32,
                    const float* resid);
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
-                 const float* bias, const float* resid, const float* ln_sums, float ln_eps, const float* col_s,
-                 float* stats_out, int M, int N, int K, int flags, cudaStream_t stream);
+                 const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
+                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream);
 void gemm_force_version(int v);
 
 int num_sms();

@@ -112,8 +112,68 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pd = ph * pw * C;
+  // Output element e = (p1*pw + p2)*C + c lives at slab[(c*ph + p1)*W + w*pw + p2].  Each lane owns the element PAIRS
+  // e = 2*lane + 64*k (so it stores 4 bytes at a time, 128 B per warp); the slab offsets of its pairs do not depend on
+  // the patch column w, so they are computed once per CTA and kept in registers together with gamma / beta.
+  constexpr int MAXP = 12;  // pairs per lane held in registers: covers patch_dim <= 768 (16x16x3)
+  const int npairs = (pd + 1) / 2;
+  int off0[MAXP], off1[MAXP];
+  float g0[MAXP], g1[MAXP], b0[MAXP], b1[MAXP];
+  const bool fast = npairs <= 32 * MAXP && (pd & 1) == 0;
+  if (fast) {
+#pragma unroll
+    for (int k = 0; k < MAXP; ++k) {
+      const int e = 2 * (lane + 32 * k);
+      off0[k] = off1[k] = -1;
+      g0[k] = g1[k] = b0[k] = b1[k] = 0.f;
+      if (e < pd) {
+        int c = e % C, pp = e / C;
+        off0[k] = (c * ph + pp / pw) * W + pp % pw;
+        g0[k] = gamma[e];
+        b0[k] = beta[e];
+        c = (e + 1) % C;
+        pp = (e + 1) / C;
+        off1[k] = (c * ph + pp / pw) * W + pp % pw;
+        g1[k] = gamma[e + 1];
+        b1[k] = beta[e + 1];
+      }
+    }
+  }
   for (int w = warp; w < gw; w += 8) {
-    // element e = (p1*pw + p2)*C + c  <->  slab[(c*ph + p1)*W + w*pw + p2]
+    __nv_bfloat16* orow = out + ((long long)(b * gh + h) * gw + w) * ldo;
+    if (fast) {
+      const __nv_bfloat16* sl = slab + w * pw;
+      float v0[MAXP], v1[MAXP];
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        v0[k] = off0[k] >= 0 ? __bfloat162float(sl[off0[k]]) : 0.f;
+        v1[k] = off1[k] >= 0 ? __bfloat162float(sl[off1[k]]) : 0.f;
+        s += v0[k] + v1[k];
+      }
+      const float mean = warp_sum(s) / (float)pd;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        const float d0 = off0[k] >= 0 ? v0[k] - mean : 0.f;
+        const float d1 = off1[k] >= 0 ? v1[k] - mean : 0.f;
+        q = fmaf(d0, d0, fmaf(d1, d1, q));
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)pd + eps);
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        const int e = 2 * (lane + 32 * k);
+        if (e < (int)ldo) {
+          uint32_t pk = 0u;  // columns [pd, ldo) are zero (K padding)
+          if (off0[k] >= 0)
+            pk = pack_bf16x2((v0[k] - mean) * rstd * g0[k] + b0[k], (v1[k] - mean) * rstd * g1[k] + b1[k]);
+          *reinterpret_cast<uint32_t*>(orow + e) = pk;
+        }
+      }
+      for (int e = 2 * 32 * MAXP + lane; e < (int)ldo; e += 32) orow[e] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    // generic path (odd patch_dim or very large patches)
     float s = 0.f;
     for (int e = lane; e < pd; e += 32) {
       const int c = e % C, pp = e / C, p2 = pp % pw, p1 = pp / pw;
@@ -127,7 +187,6 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
       q += d * d;
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)pd + eps);
-    __nv_bfloat16* orow = out + ((long long)(b * gh + h) * gw + w) * ldo;
     for (int e = lane; e < (int)ldo; e += 32) {
       float y = 0.f;
       if (e < pd) {

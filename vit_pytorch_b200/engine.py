@@ -32,8 +32,8 @@ def ln_mode() -> str:
                  deterministic, bit-exact batch-permutation equivariance).
        'fold'  : no standalone LayerNorm kernels inside the layer loop.  The residual GEMMs (out-proj, fc2) also emit
                  a bf16 copy of x plus per-row (sum, sum^2); the following GEMM multiplies that copy by gamma*W and
-                 applies  rstd*(acc - mu*colsum) + (W beta + b)  in its epilogue.  Experimental: the
-                 row statistics are accumulated with fp32 atomics, so results vary in the last bits run to run."""
+                 applies  rstd*(acc - mu*colsum) + (W beta + b)  in its epilogue.  The statistics are
+                 written as per-tile partials (no atomics) and summed in a fixed order, so results are deterministic."""
     m = os.environ.get(_LN_MODE_ENV, "exact")
     if m not in ("fold", "exact"):
         raise ValueError(f"{_LN_MODE_ENV} must be 'fold' or 'exact', got {m!r}")
@@ -177,8 +177,10 @@ class TransformerEngine:
                 "qkv": torch.empty(M, 3 * I, **bf),
                 "o": torch.empty(M, I, **bf),
                 "h": torch.empty(M, Hd, **bf),
-                "stats_a": torch.empty(M, 2, device=device, dtype=torch.float32),
-                "stats_b": torch.empty(M, 2, device=device, dtype=torch.float32),
+                # LN-fold row statistics: [M, 1, 2] written by embed_tokens / rowstats_cast, [M, parts(D), 2] by GEMMs
+                "stats_in": torch.empty(M, 1, 2, device=device, dtype=torch.float32),
+                "stats_a": torch.empty(M, _lib.stats_parts(D), 2, device=device, dtype=torch.float32),
+                "stats_b": torch.empty(M, _lib.stats_parts(D), 2, device=device, dtype=torch.float32),
             }
             self.ws_key = key
         return self.ws
@@ -187,7 +189,7 @@ class TransformerEngine:
     def run_blocks(self, x: torch.Tensor, B: int, N: int, primed: bool = False) -> None:
         """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm).
 
-        fold mode needs ws['xn'] (bf16 copy of x) and ws['stats_a'] (row sums of that copy) on entry: `primed` says
+        fold mode needs ws['xn'] (bf16 copy of x) and ws['stats_in'] (row sums of that copy) on entry: `primed` says
         the caller (embed_tokens) already wrote them, otherwise one rowstats_cast pass produces them."""
         t = self.prepared()
         M = B * N
@@ -195,10 +197,10 @@ class TransformerEngine:
         if ln_mode() == "fold":
             xb, sa, sb = ws["xn"], ws["stats_a"], ws["stats_b"]
             if not primed:
-                _lib.rowstats_cast(x, xb, sa)
+                _lib.rowstats_cast(x, xb, ws["stats_in"])
             for i, (attn, ff) in enumerate(self._layers()):
-                _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"], ln_sums=sa,
-                          col_s=t[f"{i}.qkv.s"])
+                _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
+                          ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"])
                 _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
                 _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
                           stats_out=sb)

@@ -182,7 +182,7 @@ class SimpleViT(nn.Module):
         primed = ln_mode() == "fold"
         ws = eng.workspace(B * N, img.device) if primed else None
         x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
-                                         stats=ws["stats_a"] if primed else None)
+                                         stats=ws["stats_in"] if primed else None)
         D = x.shape[1]
         eng.run_blocks(x, B, N, primed=primed)
         dev = img.device

@@ -222,7 +222,7 @@ class ViT(nn.Module):
         primed = ln_mode() == "fold"
         ws = eng.workspace(B * N, img.device) if primed else None
         x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
-                                         stats=ws["stats_a"] if primed else None)   # fp32 residual stream [B*N, D]
+                                         stats=ws["stats_in"] if primed else None)   # fp32 residual stream [B*N, D]
         D = x.shape[1]
         eng.run_blocks(x, B, N, primed=primed)
         dev = img.device
