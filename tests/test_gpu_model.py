@@ -126,6 +126,30 @@ def test_vit_b16_against_oracle(kind):
     assert mx < 0.0211 and frac > (0.90 if kind == "vit" else 0.928), (mx, mean, frac)
 
 
+@pytest.mark.parametrize("name,kwargs,floor_max,floor_frac", [
+    # BASELINE.json configs[2] / configs[3] geometry (dim_head = reference default 64); the floors are the reference's
+    # own bf16 forward against its fp32 forward, BASELINE.md section 6
+    ("ViT-L/16", dict(image_size=224, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16, mlp_dim=4096),
+     0.0249, 0.525),
+    ("ViT-H/14", dict(image_size=224, patch_size=14, num_classes=1000, dim=1280, depth=32, heads=16, mlp_dim=5120),
+     0.0257, 0.478),
+])
+def test_large_configs_against_oracle(name, kwargs, floor_max, floor_frac):
+    torch.manual_seed(0)
+    m = ViT(**kwargs).eval().bfloat16()
+    torch.manual_seed(1)
+    img = torch.randn(2, 3, 224, 224).bfloat16()
+    ref = O.vit_forward(O.upcast(m.state_dict()), kwargs, img.float())
+    m = m.to(DEV)
+    with torch.inference_mode():
+        assert m.fused_reason(img.to(DEV)) is None
+        out = m(img.to(DEV))
+    mx, mean, frac = stats(out, ref)
+    print(f"{name} vs fp32 oracle: max {mx:.5f} mean {mean:.5f} within_tol {frac:.4f} "
+          f"(reference-bf16 floor: max {floor_max}, within {floor_frac})")
+    assert mx < floor_max and frac > floor_frac, (mx, mean, frac)
+
+
 @pytest.mark.parametrize("mode", ["exact", "fold"])
 def test_full_batch_properties_b512(mode, monkeypatch):
     monkeypatch.setenv("B200VIT_LN_MODE", mode)

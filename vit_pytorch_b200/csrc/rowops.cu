@@ -89,32 +89,18 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, int C, int H, int W,
-                   int ph, int pw, float eps) {
+                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, int nrows, int C,
+                   int H, int W, int ph, int pw, float eps) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [C][ph][W]
   const int gh = H / ph, gw = W / pw;
-  const int b = blockIdx.x / gh, h = blockIdx.x % gh;
   const int slab_elems = C * ph * W;
   const int row_elems = ph * W;  // contiguous per channel in global memory
-  if ((row_elems & 7) == 0 && ((H * W) & 7) == 0) {
-    for (int i = threadIdx.x * 8; i < slab_elems; i += blockDim.x * 8) {
-      const int c = i / row_elems, r = i % row_elems;
-      const __nv_bfloat16* src = img + ((long long)(b * C + c) * H + (long long)h * ph) * W + r;
-      *reinterpret_cast<uint4*>(slab + i) = *reinterpret_cast<const uint4*>(src);
-    }
-  } else {
-    for (int i = threadIdx.x; i < slab_elems; i += blockDim.x) {
-      const int c = i / row_elems, r = i % row_elems;
-      slab[i] = img[((long long)(b * C + c) * H + (long long)h * ph) * W + r];
-    }
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pd = ph * pw * C;
   // Output element e = (p1*pw + p2)*C + c lives at slab[(c*ph + p1)*W + w*pw + p2].  Each lane owns the element PAIRS
   // e = 2*lane + 64*k (so it stores 4 bytes at a time, 128 B per warp); the slab offsets of its pairs do not depend on
-  // the patch column w, so they are computed once per CTA and kept in registers together with gamma / beta.
+  // the patch (b, h, w), so they are computed once per (persistent) CTA and kept in registers with gamma / beta.
   constexpr int MAXP = 12;  // pairs per lane held in registers: covers patch_dim <= 768 (16x16x3)
   const int npairs = (pd + 1) / 2;
   int off0[MAXP], off1[MAXP];
@@ -139,6 +125,22 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
       }
     }
   }
+  for (int bh = blockIdx.x; bh < nrows; bh += gridDim.x) {
+  const int b = bh / gh, h = bh % gh;
+  __syncthreads();  // previous slab fully consumed
+  if ((row_elems & 7) == 0 && ((H * W) & 7) == 0) {
+    for (int i = threadIdx.x * 8; i < slab_elems; i += blockDim.x * 8) {
+      const int c = i / row_elems, r = i % row_elems;
+      const __nv_bfloat16* src = img + ((long long)(b * C + c) * H + (long long)h * ph) * W + r;
+      *reinterpret_cast<uint4*>(slab + i) = *reinterpret_cast<const uint4*>(src);
+    }
+  } else {
+    for (int i = threadIdx.x; i < slab_elems; i += blockDim.x) {
+      const int c = i / row_elems, r = i % row_elems;
+      slab[i] = img[((long long)(b * C + c) * H + (long long)h * ph) * W + r];
+    }
+  }
+  __syncthreads();
   for (int w = warp; w < gw; w += 8) {
     __nv_bfloat16* orow = out + ((long long)(b * gh + h) * gw + w) * ldo;
     if (fast) {
@@ -196,6 +198,7 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
       orow[e] = __float2bfloat16_rn(y);
     }
   }
+  }  // persistent loop over (image, patch row)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -363,9 +366,13 @@ extern "C" int b200vit_patchify_ln(const void* img, const float* gamma, const fl
     B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  patchify_ln_kernel<<<B * (H / ph), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, C, H,
-      W, ph, pw, eps);
+  const int nrows = B * (H / ph);
+  const int per_sm = (int)(200 * 1024 / (smem + 1024)) < 8 ? (int)(200 * 1024 / (smem + 1024)) : 8;
+  int grid = num_sms() * (per_sm < 1 ? 1 : per_sm);
+  if (grid > nrows) grid = nrows;
+  patchify_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, nrows,
+      C, H, W, ph, pw, eps);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
