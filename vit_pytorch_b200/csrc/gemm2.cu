@@ -42,8 +42,8 @@ struct Cfg {
   static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
   static constexpr int EPI_BYTES = EPI_WARPS * BUFS_PER_WARP * EPI_BUF_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_BYTES;
-  // full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[EPI_WARPS][2] + tmem ptr
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS;
+  // full[S] empty[S] tmem_full[2] tmem_empty[2] resid_full[EPI_WARPS][2] out_ready[EPI_WARPS][2] bbuf_free[EPI_WARPS]
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 5 * EPI_WARPS;
   static constexpr int DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
 };
 }  // namespace g2
@@ -107,8 +107,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* resid_full = tmem_empty + 2;  // [EPI_WARPS][2]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(resid_full + 2 * EPI_WARPS);
+  uint64_t* resid_full = tmem_empty + 2;             // [EPI_WARPS][2] staging box b holds its input / is free
+  uint64_t* out_ready = resid_full + 2 * EPI_WARPS;  // [EPI_WARPS][2] staging box b holds finished output
+  uint64_t* bbuf_free = out_ready + 2 * EPI_WARPS;   // [EPI_WARPS]    bf16 copy box has been stored (MODE_DUAL)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bbuf_free + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,7 +133,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
     }
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resid_full[i], 1);
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) {
+      mbar_init(&resid_full[i], 1);
+      mbar_init(&out_ready[i], 1);
+    }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&bbuf_free[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -204,6 +210,56 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           acc = 0;
           acc_phase ^= 1;
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ epilogue TMA lanes (MODE_F32 / MODE_DUAL)
+    // Lane e moves the staging boxes of epilogue warp e: it stores finished boxes, waits until the store engine has
+    // read them and refills the buffer with the residual box two steps ahead (or just marks it free).  The epilogue
+    // warps themselves never block on a TMA store.
+    if constexpr (MODE != MODE_BF16) {
+      if (lane < EPI_WARPS) {
+        const int e = lane;
+        const int quad = e & 3;
+        const int col_off = (e >> 2) * COLS_PER_WARP;
+        constexpr int BOXES = COLS_PER_WARP / 32;
+        const bool has_resid = (p.flags & B200VIT_EPI_RESIDUAL) != 0;
+        uint8_t* buf0 = epi_smem + e * C::BUFS_PER_WARP * EPI_BUF_BYTES;
+        uint8_t* bbuf = buf0 + 2 * EPI_BUF_BYTES;
+        const int my_tiles = cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+        const uint32_t total = static_cast<uint32_t>(my_tiles) * BOXES;
+        auto coords = [&](uint32_t g, int& cc, int& cr) {
+          const int tile = cluster_id + static_cast<int>(g / BOXES) * num_clusters;
+          const int m_pair = tile / p.num_n_tiles;
+          const int n_blk = tile % p.num_n_tiles;
+          cr = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
+          cc = n_blk * BLOCK_N + col_off + static_cast<int>(g % BOXES) * 32;
+        };
+        auto refill = [&](uint32_t g) {  // make buffer g & 1 ready for box g
+          uint64_t* bar = &resid_full[2 * e + (g & 1)];
+          if (has_resid) {
+            int cc, cr;
+            coords(g, cc, cr);
+            mbar_arrive_expect_tx(bar, EPI_BUF_BYTES);
+            tma_load_2d(buf0 + (g & 1) * EPI_BUF_BYTES, &tmResid, bar, cc, cr);
+          } else {
+            mbar_arrive(bar);
+          }
+        };
+        if (total > 0) refill(0);
+        if (total > 1) refill(1);
+        for (uint32_t g = 0; g < total; ++g) {
+          mbar_wait(&out_ready[2 * e + (g & 1)], (g >> 1) & 1);
+          int cc, cr;
+          coords(g, cc, cr);
+          tma_store_2d(&tmOut, buf0 + (g & 1) * EPI_BUF_BYTES, cc, cr);
+          if (MODE == MODE_DUAL && (g & 1)) tma_store_2d(&tmOutB, bbuf, cc - 32, cr);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          if (MODE == MODE_DUAL && (g & 1)) mbar_arrive(&bbuf_free[e]);
+          if (g + 2 < total) refill(g + 2);
+        }
+        tma_store_wait<0>();  // all global writes complete before exit
       }
     }
   } else if (warp >= 4) {
@@ -297,30 +353,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr bool DUAL = MODE == MODE_DUAL;
       const bool has_resid = (flags & B200VIT_EPI_RESIDUAL) != 0;
       uint8_t* bbuf = buf0 + 2 * EPI_BUF_BYTES;  // DUAL only: bf16 copy staging box (64 columns)
-      uint64_t* rbar = resid_full + 2 * e;
+      uint64_t* in_bar = resid_full + 2 * e;
+      uint64_t* out_bar = out_ready + 2 * e;
       uint32_t box_seq = 0;  // running count of fp32 boxes used by this warp (buffer = box_seq & 1)
       float st_sum = 0.f, st_sq = 0.f;
-
-      auto box_coords = [&](int tile, int box, int& c_col, int& c_row) {
-        const int m_pair = tile / p.num_n_tiles;
-        const int n_blk = tile % p.num_n_tiles;
-        c_row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
-        c_col = n_blk * BLOCK_N + col_off + box * 32;
-      };
-      // residual prefetch of box `seq` (stream order over this CTA's tiles) into buffer seq & 1
-      auto prefetch_resid = [&](int tile, int box, uint32_t seq) {
-        if (lane == 0) {
-          int cc, cr;
-          box_coords(tile, box, cc, cr);
-          tma_store_wait_read<0>();  // the store that last used this buffer has finished reading it
-          mbar_arrive_expect_tx(&rbar[seq & 1], EPI_BUF_BYTES);
-          tma_load_2d(buf0 + (seq & 1) * EPI_BUF_BYTES, &tmResid, &rbar[seq & 1], cc, cr);
-        }
-      };
-      if (has_resid && cluster_id < num_tiles) {
-        prefetch_resid(cluster_id, 0, 0);
-        prefetch_resid(cluster_id, 1, 1);
-      }
 
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_pair = tile / p.num_n_tiles;
@@ -355,8 +391,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           epilogue_math<32>(v, n_blk * BLOCK_N + col_off + c, flags, mu, rstd, p);
 
           uint8_t* myrow = my_row0 + (box_seq & 1) * EPI_BUF_BYTES;
+          mbar_wait(&in_bar[box_seq & 1], (box_seq >> 1) & 1);  // residual box landed / buffer free
           if (has_resid) {
-            mbar_wait(&rbar[box_seq & 1], (box_seq >> 1) & 1);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float4* sp = reinterpret_cast<float4*>(myrow + ((static_cast<uint32_t>(q) ^ sw) << 4));
@@ -370,6 +406,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (DUAL) {
               // bf16 copy of the new residual rows (A operand of the next, LN-folded GEMM) + its row statistics
               const int half = (c >> 5) & 1;
+              if (half == 0) mbar_wait(&bbuf_free[e], ((box_seq >> 1) & 1) ^ 1);  // previous pair's store has read it
               uint8_t* brow = bbuf + lane * 128;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -390,8 +427,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           } else {
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               *reinterpret_cast<float4*>(myrow + ((static_cast<uint32_t>(q) ^ sw) << 4)) =
@@ -399,22 +434,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            int cc, cr;
-            box_coords(tile, c >> 5, cc, cr);
-            tma_store_2d(&tmOut, buf0 + (box_seq & 1) * EPI_BUF_BYTES, cc, cr);
-            if (DUAL && ((c >> 5) & 1)) tma_store_2d(&tmOutB, bbuf, cc - 32, cr);
-            tma_store_commit();
-          }
-          if (has_resid) {
-            // prefetch the residual box that will use this buffer next (two boxes ahead in stream order)
-            int nbox = (c >> 5) + 2, ntile = tile;
-            if (nbox >= COLS_PER_WARP / 32) {
-              nbox -= COLS_PER_WARP / 32;
-              ntile += num_clusters;
-            }
-            if (ntile < num_tiles) prefetch_resid(ntile, nbox, box_seq + 2);
-          }
+          if (lane == 0) mbar_arrive(&out_bar[box_seq & 1]);  // the TMA lane stores it and recycles the buffer
           ++box_seq;
         }
         if (DUAL && row_ok) {
@@ -428,7 +448,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-    if (lane == 0) tma_store_wait<0>();  // all global writes of this warp complete before exit
+    if (MODE == MODE_BF16 && lane == 0) tma_store_wait<0>();  // all global writes of this warp complete before exit
   }
 
   // ------------------------------------------------------------------ teardown
