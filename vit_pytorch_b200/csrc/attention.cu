@@ -114,45 +114,68 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);  // B = V is MN-major
-      int it = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+      // S_t(it) = Q_t K^T into region t  (waits until the epilogue of unit it-1 has drained the region)
+      auto issue_s = [&](int it, int t) {
         const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const uint32_t up = it & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
         const uint32_t sk = smem_u32(smem + s * stage_bytes);
-        const uint32_t sv = sk + kv_bytes;
-        const uint32_t sq = sv + kv_bytes;
-        // S_t = Q_t K^T
-        for (int t = 0; t < NWG; ++t) {
-          mbar_wait(&o_free[t], up ^ 1);  // region t drained by the previous unit's epilogue
-          tc_fence_after();
-          const uint32_t d_s = tmem_base + t * REGION;
-          for (int n0 = 0; n0 < p.KP; n0 += 256) {
-            const int nn = (p.KP - n0) < 256 ? (p.KP - n0) : 256;
-            const uint32_t idesc_s = make_idesc_bf16(128, nn, 0, 0);
-            const uint64_t adesc = make_smem_desc_sw128(sq + t * Q_TILE_BYTES, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sk + n0 * 128, 16, 1024);
+        const uint32_t sq = sk + 2 * kv_bytes;
+        mbar_wait(&o_free[t], (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_s = tmem_base + t * REGION;
+        for (int n0 = 0; n0 < p.KP; n0 += 256) {
+          const int nn = (p.KP - n0) < 256 ? (p.KP - n0) : 256;
+          const uint32_t idesc_s = make_idesc_bf16(128, nn, 0, 0);
+          const uint64_t adesc = make_smem_desc_sw128(sq + t * Q_TILE_BYTES, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sk + n0 * 128, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          }
-          umma_commit(&s_full[t]);
+          for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         }
-        // O_t = P_t V
-        for (int t = 0; t < NWG; ++t) {
-          mbar_wait(&p_ready[t], up);
-          tc_fence_after();
-          const uint32_t d_o = tmem_base + t * REGION + O_COL;
-          const int ksteps = p.KP / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            // 16 keys = two 8-row groups of V = 2048 B
-            const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
-            umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);  // A = P from TMEM
-          }
-          umma_commit(&o_full[t]);
+        umma_commit(&s_full[t]);
+      };
+      // O_t(it) = P_t V  (A = P from TMEM, B = V as MN-major smem operand: 16 keys = two 8-row groups = 2048 B)
+      auto issue_pv = [&](int it, int t) {
+        const int s = it % STAGES;
+        const uint32_t sv = smem_u32(smem + s * stage_bytes) + kv_bytes;
+        mbar_wait(&p_ready[t], it & 1);
+        tc_fence_after();
+        const uint32_t d_o = tmem_base + t * REGION + O_COL;
+        const int ksteps = p.KP / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
+          umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
         }
-        umma_commit(&empty_bar[s]);  // K/V/Q of this stage no longer needed once everything above completed
+        umma_commit(&o_full[t]);
+      };
+      auto wait_full = [&](int it) {
+        mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);
+        tc_fence_after();
+      };
+      const int n_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      if (NWG == 2 && STAGES == 2) {
+        // Skewed schedule: the two warpgroups run half a unit out of phase, so that one of them is in its softmax
+        // while the other waits for its PV / next S MMAs:
+        //     S0(0) | S1(i)  PV0(i)  S0(i+1)  PV1(i) | ...
+        if (n_units > 0) {
+          wait_full(0);
+          issue_s(0, 0);
+        }
+        for (int it = 0; it < n_units; ++it) {
+          issue_s(it, 1);
+          issue_pv(it, 0);
+          if (it + 1 < n_units) {
+            wait_full(it + 1);
+            issue_s(it + 1, 0);
+          }
+          issue_pv(it, 1);
+          umma_commit(&empty_bar[it % STAGES]);  // every MMA reading this K/V/Q stage has been issued before
+        }
+      } else {
+        for (int it = 0; it < n_units; ++it) {
+          wait_full(it);
+          for (int t = 0; t < NWG; ++t) issue_s(it, t);
+          for (int t = 0; t < NWG; ++t) issue_pv(it, t);
+          umma_commit(&empty_bar[it % STAGES]);
+        }
       }
     }
   } else {
