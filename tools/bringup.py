@@ -287,14 +287,14 @@ CASES = {
     "embed_nocls": lambda: case_embed(4, 64, 0, 192),
     "pool_cast": lambda: case_pool(8, 197, 768),
     "attn_tmem_197": lambda: case_attention(4, 197, 12, psmem=0),
-    "attn_smem_197": lambda: case_attention(4, 197, 12, psmem=1),
     "attn_tmem_64": lambda: case_attention(4, 64, 3, psmem=0),
-    "attn_smem_64": lambda: case_attention(4, 64, 3, psmem=1),
     "attn_tmem_257": lambda: case_attention(2, 257, 16, psmem=0),
-    "attn_smem_257": lambda: case_attention(2, 257, 16, psmem=1),
     "attn_tmem_50": lambda: case_attention(3, 50, 4, psmem=0),
     "attn_tmem_big": lambda: case_attention(512, 197, 12, psmem=0, time_it=True),
-    "attn_smem_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True),
+    "attn_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True),
+    "attn_1cta_197": lambda: case_attention(4, 197, 12, psmem=1),
+    "attn_tmem_129": lambda: case_attention(3, 129, 2, psmem=0),
+    "attn_tmem_256": lambda: case_attention(2, 256, 2, psmem=0),
 }
 
 

@@ -34,11 +34,14 @@ struct AttnParams {
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
 
-template <int NWG, int STAGES>
-__global__ void __launch_bounds__((4 * NWG + 2) * 32, 1)
+// TMEM_COLS = 512: one CTA per SM (NWG regions of 512/NWG columns).  TMEM_COLS = 256 (NWG = 1, one K/V/Q stage):
+// TWO independent CTAs per SM, each with one softmax warpgroup -- while one CTA waits for its MMAs or loads, the
+// other one's softmax keeps the MUFU / issue slots busy.
+template <int NWG, int STAGES, int TMEM_COLS>
+__global__ void __launch_bounds__((4 * NWG + 2) * 32, TMEM_COLS == 256 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttnParams p) {
-  constexpr int REGION = 512 / NWG;
+  constexpr int REGION = TMEM_COLS / NWG;
   constexpr int O_COL = REGION - ATT_DH;
   constexpr int NUM_SOFTMAX_WARPS = 4 * NWG;
   constexpr int Q_TILE_BYTES = 128 * 128;
@@ -77,7 +80,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
-    tmem_alloc(tmem_base_smem, 512);
+    tmem_alloc(tmem_base_smem, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -322,24 +325,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // debug / experiment knobs (b200vit_debug_set)
+static int g_attn_mode = 0;      // 0 auto (two CTAs / SM when possible), 1 force the one-CTA-per-SM variants
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 
-template <int NWG, int STAGES>
+template <int NWG, int STAGES, int TMEM_COLS = 512>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, size_t smem_bytes,
                             cudaStream_t stream) {
-  auto kern = attention_kernel<NWG, STAGES>;
+  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS>;
   static size_t smem_set = 0;
   if (smem_bytes > smem_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     smem_set = smem_bytes;
   }
-  const int grid = p.units < num_sms() ? p.units : num_sms();
+  const int slots = num_sms() * (TMEM_COLS == 256 ? 2 : 1);
+  const int grid = p.units < slots ? p.units : slots;
   kern<<<grid, (4 * NWG + 2) * 32, smem_bytes, stream>>>(tmQ, tmKV, p);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -352,7 +357,7 @@ using namespace b200;
 
 extern "C" int b200vit_debug_set(int key, int value) {
   switch (key) {
-    case 1: return 0;  // (retired: P staging through shared memory)
+    case 1: g_attn_mode = value; return 0;
     case 2: g_attn_v_lbo = value; return 0;
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
@@ -371,7 +376,9 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.B = B; p.N = N; p.H = H;
   p.I = H * dh;
   p.KP = (N + 15) / 16 * 16;
-  const int nwg = (N > 128 && p.KP <= 256) ? 2 : 1;
+  // occupancy 2 (two single-warpgroup CTAs per SM, 256 TMEM columns each) whenever one region can hold S | P | O
+  const bool occ2 = g_attn_mode != 1 && p.KP <= 256;
+  const int nwg = occ2 ? 1 : ((N > 128 && p.KP <= 256) ? 2 : 1);
   p.kv_boxes = (p.KP + 255) / 256;
   p.kv_box_rows = ((p.KP + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
   const int q_tiles = (N + 127) / 128;
@@ -398,11 +405,12 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   const size_t kv_bytes = (size_t)att_kv_bytes(p.kv_boxes, p.kv_box_rows);
   const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * 128 * 128;
   auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
-  // two K/V/Q stages when they fit (prefetch of the next unit), else one
-  const int stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
+  // two K/V/Q stages when they fit (prefetch of the next unit), else one; the occupancy-2 variant uses one
+  const int stages = (!occ2 && smem_for(2) <= 227 * 1024) ? 2 : 1;
   const size_t smem_bytes = smem_for(stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (occ2 && smem_bytes <= 113 * 1024) return launch_attention<1, 1, 256>(tmQ, tmKV, p, smem_bytes, st);
   if (nwg == 2) {
     if (stages == 1) return launch_attention<2, 1>(tmQ, tmKV, p, smem_bytes, st);
     return launch_attention<2, 2>(tmQ, tmKV, p, smem_bytes, st);
