@@ -301,7 +301,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_src} sustained",
                 "avg_launch_ms": g["ms"] / g["launches"], "launches_per_step": g["launches"] // nprof}
 
@@ -326,6 +326,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                                 else f"{args.model} 224^2 forward, dim_head 64"), "batch_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2_policy": "inputs (154 MB/step) and activations (GBs/step) exceed the 126 MB L2",
+                   "ln_mode": os.environ.get("B200VIT_LN_MODE", "fold"),
                    "weights": "random init, torch.manual_seed(0)"},
         "tflops_per_gpu": tf,
         "frac_of_bf16_burst_peak": tf / float(peaks["bf16_tflops"]),

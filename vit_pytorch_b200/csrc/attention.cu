@@ -30,6 +30,7 @@ struct AttnParams {
   float scale_log2e;
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
+  int skip_max;           // experiment: skip the row-max pass (max := 0)
 };
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
@@ -216,7 +217,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     m3 = fmaxf(m3, __uint_as_float(R[j + 3]));                          \
   }
         int ci = 0;
-        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
+        if (p.skip_max) {
+          m0 = m1 = m2 = m3 = 0.f;
+          ci = 1 << 20;
+        }
+        if (!p.skip_max && nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
           tmem_ld_wait();
           tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
@@ -229,7 +234,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_wait();
           ATT_MAX32(ra)
         }
-        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
+        for (int c0 = nfull * 32; c0 < p.KP && !p.skip_max; c0 += 16) {
           uint32_t r16[16];
           tmem_ld_32x32b_x16(t_lane + c0, r16);
           tmem_ld_wait();
@@ -331,6 +336,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // debug / experiment knobs (b200vit_debug_set)
 static int g_attn_mode = 0;      // 0 auto (two CTAs / SM when possible), 1 force the one-CTA-per-SM variants
+static int g_attn_skip_max = 0;  // experiment only
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 
@@ -361,6 +367,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 2: g_attn_v_lbo = value; return 0;
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
+    case 5: g_attn_skip_max = value; return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }
@@ -386,6 +393,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.units = B * H * p.rounds;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.skip_max = g_attn_skip_max;
   p.v_lbo = (unsigned)g_attn_v_lbo;
   p.v_sbo = (unsigned)g_attn_v_sbo;
 
