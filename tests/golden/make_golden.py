@@ -89,6 +89,38 @@ def make(name: str, spec: dict) -> None:
           f"ref-bf16 max err {(logits_bf16.float() - logits).abs().max():.5f}; {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def make_navit() -> None:
+    """NaViT (reference na_vit.py): 7 images of 5 different resolutions, given as two pre-packed rows AND re-packed by
+    the reference's own greedy grouping; fp32 logits of both calls are stored."""
+    from vit_pytorch.na_vit import NaViT
+    kwargs = dict(image_size=64, patch_size=8, num_classes=11, dim=128, depth=2, heads=2, mlp_dim=192, dim_head=64)
+    torch.manual_seed(5)
+    model = NaViT(**kwargs).eval()
+    g = torch.Generator().manual_seed(1005)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            p.copy_(p.bfloat16().float())
+    torch.manual_seed(105)
+    sizes = [(64, 64), (32, 48), (16, 16), (64, 32), (24, 40), (8, 64), (48, 48)]
+    imgs = [torch.randn(3, h, w).bfloat16() for h, w in sizes]
+    rows = [[0, 1, 2], [3, 4, 5, 6]]
+    with torch.inference_mode():
+        packed = model([[imgs[i].float() for i in r] for r in rows])
+        grouped = model([im.float() for im in imgs], group_images=True, group_max_seq_len=80)
+    blob = {"name": "navit_tiny", "kind": "navit", "kwargs": kwargs,
+            "state_dict": {k: v.bfloat16() for k, v in model.state_dict().items()},
+            "images": imgs, "rows": rows, "group_max_seq_len": 80,
+            "logits_fp32": packed.clone(), "logits_grouped_fp32": grouped.clone(),
+            "versions": {"torch": str(torch.__version__), "reference": "vit-pytorch 1.23.6 @ /root/reference"}}
+    path = os.path.join(HERE, "navit_tiny.pt")
+    torch.save(blob, path)
+    print(f"navit_tiny: logits {tuple(packed.shape)} |max| {packed.abs().max():.4f}; packed vs grouped "
+          f"{(packed - grouped).abs().max():.2e}; {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     for n, s in CASES.items():
         make(n, s)
+    make_navit()

@@ -1,0 +1,79 @@
+"""NaViT (reference na_vit.py): oracle and host-side mirror against outputs of the reference (CPU)."""
+import pytest
+import torch
+
+from conftest import import_reference, load_golden, reference_available
+from oracle import navit_oracle as NO
+from oracle import vit_oracle as O
+from vit_pytorch_b200.na_vit import NaViT, group_images_by_max_seq_len
+
+
+@pytest.fixture(scope="module")
+def g():
+    return load_golden("navit_tiny")
+
+
+def test_oracle_per_image_equals_reference_packed(g):
+    """The unpacked, mask-free per-image restatement reproduces the reference's packed + masked forward."""
+    sd = O.upcast(g["state_dict"])
+    imgs = [im.float() for im in g["images"]]
+    out = NO.navit_forward(sd, g["kwargs"], [[imgs[i] for i in r] for r in g["rows"]])
+    assert out.shape == g["logits_fp32"].shape
+    assert torch.allclose(out, g["logits_fp32"], rtol=1e-4, atol=2e-5), (out - g["logits_fp32"]).abs().max()
+    # packing is irrelevant to the result: the reference's own greedy re-grouping gives the same logits
+    assert torch.allclose(out, g["logits_grouped_fp32"], rtol=1e-4, atol=2e-5)
+
+
+def test_grouping_matches_reference_rule(g):
+    imgs = g["images"]
+    ours = group_images_by_max_seq_len(imgs, 8, max_seq_len=g["group_max_seq_len"])
+    orc = NO.group_images_by_max_seq_len(imgs, 8, max_seq_len=g["group_max_seq_len"])
+    sizes = lambda groups: [[tuple(im.shape[-2:]) for im in grp] for grp in groups]
+    assert sizes(ours) == sizes(orc)
+    toks = [[(im.shape[-2] // 8) * (im.shape[-1] // 8) for im in grp] for grp in ours]
+    assert all(sum(t) <= 80 for t in toks) and sum(len(t) for t in toks) == len(imgs)
+    with pytest.raises(AssertionError, match="exceeds maximum sequence length"):
+        group_images_by_max_seq_len([torch.zeros(3, 64, 64)], 8, max_seq_len=10)
+
+
+def test_module_state_dict_and_forward(g):
+    m = NaViT(**g["kwargs"]).eval()
+    assert list(m.state_dict().keys()) == list(g["state_dict"].keys())
+    m.load_state_dict(g["state_dict"])
+    m = m.float()
+    imgs = [im.float() for im in g["images"]]
+    with torch.inference_mode():
+        packed = m([[imgs[i] for i in r] for r in g["rows"]])
+        grouped = m(imgs, group_images=True, group_max_seq_len=g["group_max_seq_len"])
+        single_row = m(imgs[:3])                                   # List[Tensor] = one row
+    assert torch.allclose(packed, g["logits_fp32"], rtol=1e-4, atol=2e-5)
+    assert torch.allclose(grouped, g["logits_grouped_fp32"], rtol=1e-4, atol=2e-5)
+    assert torch.allclose(single_row, g["logits_fp32"][:3], rtol=1e-4, atol=2e-5)
+    assert m.fused_reason() is not None                            # sm_100a path not built yet: stated, not hidden
+
+
+def test_patch_order_is_channel_major():
+    img = torch.arange(3 * 4 * 6, dtype=torch.float32).reshape(3, 4, 6)
+    p = NO.patchify_cpp(img, 2)
+    # token (h=1, w=2), element (c=2, p1=1, p2=0)
+    assert p[1 * 3 + 2, (2 * 2 + 1) * 2 + 0] == img[2, 1 * 2 + 1, 2 * 2 + 0]
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present (GPU box)")
+def test_same_seed_init_and_live_reference():
+    import importlib
+    import_reference()
+    RefNaViT = importlib.import_module("vit_pytorch.na_vit").NaViT
+    kwargs = dict(image_size=32, patch_size=8, num_classes=5, dim=64, depth=1, heads=2, mlp_dim=96, dim_head=32)
+    torch.manual_seed(9)
+    a = RefNaViT(**kwargs).eval()
+    torch.manual_seed(9)
+    b = NaViT(**kwargs).eval()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    imgs = [torch.randn(3, 32, 16), torch.randn(3, 8, 8), torch.randn(3, 24, 32)]
+    with torch.inference_mode():
+        want = a([imgs[:2], imgs[2:]])
+        got = b([imgs[:2], imgs[2:]])
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(NO.navit_forward(O.upcast(sa), kwargs, [imgs[:2], imgs[2:]]), want, rtol=1e-4, atol=1e-5)

@@ -6,6 +6,7 @@ The fused path lives in csrc/ (CUDA, C ABI in include/b200vit.h) and is bound wi
 """
 from .vit import ViT
 from .simple_vit import SimpleViT
+from .na_vit import NaViT           # interface mirror + PyTorch graph; its sm_100a path is the next row
 
-__all__ = ["ViT", "SimpleViT"]
+__all__ = ["ViT", "SimpleViT", "NaViT"]
 __version__ = "0.1.0"

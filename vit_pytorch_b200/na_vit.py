@@ -1,0 +1,226 @@
+"""Drop-in `NaViT` for `vit_pytorch.na_vit.NaViT` (reference na_vit.py:195-402): host-side mirror.
+
+Same constructor keywords, parameter / buffer names, shapes and registration order (bias-free `LayerNorm` with a
+`gamma` parameter and a zero `beta` buffer, per-head q/k `RMSNorm`, factorised height / width positional tables,
+attention pooling with one learned query, bias-free head), same `forward(List[Tensor] | List[List[Tensor]],
+group_images=False, group_max_seq_len=2048) -> (num_images, num_classes)` and the same greedy packing helper.
+
+STATUS: this file is the interface mirror + PyTorch graph only.  The sm_100a path for it --
+a varlen (cu_seqlens) block-diagonal attention kernel with a key-block loop, the q/k RMSNorm prologue and the
+attention-pool kernel -- is the next row to build; `fused_reason()` says so and forward() always runs the graph below.
+
+Formulation: the reference pads packed rows and separates images with an O(B L^2) boolean mask.  Here every packed row
+is described by per-token image ids (the varlen description a kernel wants) and the mask is built once per call from
+them; arithmetic and outputs are identical (tests/test_navit.py against reference goldens).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Union
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+
+def group_images_by_max_seq_len(images: Sequence[Tensor], patch_size: int,
+                                calc_token_dropout: Union[None, float, Callable] = None,
+                                max_seq_len: int = 2048) -> List[List[Tensor]]:
+    """Greedy packing in arrival order: open a new row when the next image does not fit (reference na_vit.py:38-77)."""
+    if calc_token_dropout is None:
+        drop = lambda h, w: 0.0
+    elif isinstance(calc_token_dropout, (float, int)):
+        drop = lambda h, w, v=float(calc_token_dropout): v
+    else:
+        drop = calc_token_dropout
+    rows: List[List[Tensor]] = []
+    row: List[Tensor] = []
+    used = 0
+    for image in images:
+        assert isinstance(image, Tensor)
+        h, w = image.shape[-2:]
+        n = int((h // patch_size) * (w // patch_size) * (1 - drop(h, w)))
+        assert n <= max_seq_len, f'image with dimensions {(h, w)} exceeds maximum sequence length'
+        if used + n > max_seq_len:
+            rows.append(row)
+            row, used = [], 0
+        row.append(image)
+        used += n
+    if row:
+        rows.append(row)
+    return rows
+
+
+class LayerNorm(nn.Module):
+    """LayerNorm with learned scale and no learned shift (reference na_vit.py:82-89)."""
+
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer('beta', torch.zeros(dim))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.layer_norm(x, x.shape[-1:], self.gamma, self.beta)
+
+
+class RMSNorm(nn.Module):
+    """Per-head query/key normalisation: unit L2 norm * sqrt(dim) * gamma[h, 1, d] (reference na_vit.py:93-101)."""
+
+    def __init__(self, heads: int, dim: int) -> None:
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(heads, 1, dim))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.normalize(x, dim=-1) * self.scale * self.gamma
+
+
+def FeedForward(dim: int, hidden_dim: int, dropout: float = 0.) -> nn.Sequential:
+    return nn.Sequential(LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                         nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class Attention(nn.Module):
+    """Self / cross attention with q/k RMSNorm and softmax scale 1 (reference na_vit.py:115-169)."""
+
+    def __init__(self, dim: int, heads: int = 8, dim_head: int = 64, dropout: float = 0.) -> None:
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.heads = heads
+        self.norm = LayerNorm(dim)
+        self.q_norm = RMSNorm(heads, dim_head)
+        self.k_norm = RMSNorm(heads, dim_head)
+        self.dropout_p = dropout
+        self.to_q = nn.Linear(dim, inner_dim, bias=False)
+        self.to_kv = nn.Linear(dim, inner_dim * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim, bias=False), nn.Dropout(dropout))
+
+    def forward(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                attn_mask: Optional[Tensor] = None) -> Tensor:
+        x = self.norm(x)
+        src = x if context is None else context
+        b, n, _ = x.shape
+        h = self.heads
+        q = self.to_q(x).reshape(b, n, h, -1).transpose(1, 2)
+        kv = self.to_kv(src).reshape(b, src.shape[1], 2, h, -1).permute(2, 0, 3, 1, 4)
+        q, k, v = self.q_norm(q), self.k_norm(kv[0]), kv[1]
+        if mask is not None:
+            key_mask = mask[:, None, None, :]
+            attn_mask = key_mask if attn_mask is None else (attn_mask & key_mask)
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask,
+                                             dropout_p=self.dropout_p if self.training else 0., scale=1.)
+        return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int, dropout: float = 0.) -> None:
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout),
+                FeedForward(dim, mlp_dim, dropout=dropout),
+            ]))
+        self.norm = LayerNorm(dim)
+
+    def forward(self, x: Tensor, mask: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None) -> Tensor:
+        for attn, ff in self.layers:
+            x = attn(x, mask=mask, attn_mask=attn_mask) + x
+            x = ff(x) + x
+        return self.norm(x)
+
+
+class NaViT(nn.Module):
+    def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, channels=3, dim_head=64,
+                 dropout=0., emb_dropout=0., token_dropout_prob=None) -> None:
+        super().__init__()
+        image_height, image_width = image_size if isinstance(image_size, tuple) else (image_size, image_size)
+        self.calc_token_dropout = None
+        if callable(token_dropout_prob):
+            self.calc_token_dropout = token_dropout_prob
+        elif isinstance(token_dropout_prob, (float, int)):
+            assert 0. <= token_dropout_prob < 1.
+            token_dropout_prob = float(token_dropout_prob)
+            self.calc_token_dropout = lambda height, width: token_dropout_prob
+        assert image_height % patch_size == 0 and image_width % patch_size == 0, \
+            'Image dimensions must be divisible by the patch size.'
+        patch_dim = channels * (patch_size ** 2)
+        self.channels = channels
+        self.patch_size = patch_size
+        self.to_patch_embedding = nn.Sequential(LayerNorm(patch_dim), nn.Linear(patch_dim, dim), LayerNorm(dim))
+        self.pos_embed_height = nn.Parameter(torch.randn(image_height // patch_size, dim))
+        self.pos_embed_width = nn.Parameter(torch.randn(image_width // patch_size, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.attn_pool_queries = nn.Parameter(torch.randn(dim))
+        self.attn_pool = Attention(dim=dim, dim_head=dim_head, heads=heads)
+        self.to_latent = nn.Identity()
+        self.mlp_head = nn.Sequential(LayerNorm(dim), nn.Linear(dim, num_classes, bias=False))
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def fused_reason(self, batched_images=None) -> Optional[str]:
+        return "NaViT's sm_100a path (varlen block-diagonal attention, q/k RMSNorm, attention pooling) is not built yet"
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _tokenise_row(self, images: Sequence[Tensor], training_dropout: bool):
+        """One packed row: patch vectors in (c p1 p2) order, (h, w) grid positions and image ids per token."""
+        p, c, dev = self.patch_size, self.channels, self.device
+        seqs, poss, ids = [], [], []
+        for i, img in enumerate(images):
+            assert img.ndim == 3 and img.shape[0] == c
+            hh, ww = img.shape[-2:]
+            assert hh % p == 0 and ww % p == 0, f'height and width {(hh, ww)} of images must be divisible by patch size {p}'
+            gh, gw = hh // p, ww // p
+            seq = img.reshape(c, gh, p, gw, p).permute(1, 3, 0, 2, 4).reshape(gh * gw, c * p * p)
+            pos = torch.stack([torch.arange(gh, device=dev).repeat_interleave(gw),
+                               torch.arange(gw, device=dev).repeat(gh)], dim=-1)
+            if training_dropout:
+                rate = self.calc_token_dropout(hh, ww)
+                keep = max(1, int(seq.shape[0] * (1 - rate)))
+                idx = torch.randn((seq.shape[0],), device=dev).topk(keep, dim=-1).indices
+                seq, pos = seq[idx], pos[idx]
+            seqs.append(seq)
+            poss.append(pos)
+            ids.append(torch.full((seq.shape[0],), i, device=dev, dtype=torch.long))
+        return torch.cat(seqs), torch.cat(poss), torch.cat(ids)
+
+    def forward(self, batched_images: Union[List[Tensor], List[List[Tensor]]], group_images: bool = False,
+                group_max_seq_len: int = 2048) -> Tensor:
+        dev = self.device
+        training_dropout = self.calc_token_dropout is not None and self.training
+        if group_images:
+            batched_images = group_images_by_max_seq_len(
+                batched_images, patch_size=self.patch_size,
+                calc_token_dropout=self.calc_token_dropout if self.training else None, max_seq_len=group_max_seq_len)
+        if torch.is_tensor(batched_images[0]):
+            batched_images = [batched_images]
+
+        rows = [self._tokenise_row(images, training_dropout) for images in batched_images]
+        counts = torch.tensor([len(images) for images in batched_images], device=dev)
+        lengths = torch.tensor([r[0].shape[0] for r in rows], device=dev)
+        L = int(lengths.max())
+        B = len(rows)
+        patches = torch.zeros(B, L, rows[0][0].shape[1], device=dev, dtype=rows[0][0].dtype)
+        positions = torch.zeros(B, L, 2, device=dev, dtype=torch.long)
+        image_ids = torch.zeros(B, L, device=dev, dtype=torch.long)      # padding carries id 0, like pad_sequence
+        for b, (seq, pos, ids) in enumerate(rows):
+            n = seq.shape[0]
+            patches[b, :n], positions[b, :n], image_ids[b, :n] = seq, pos, ids
+        valid = torch.arange(L, device=dev)[None, :] < lengths[:, None]                       # key padding mask
+        attn_mask = (image_ids[:, None, :, None] == image_ids[:, None, None, :]) & valid[:, None, None, :]
+
+        x = self.to_patch_embedding(patches)
+        x = x + self.pos_embed_height[positions[..., 0]] + self.pos_embed_width[positions[..., 1]]
+        x = self.dropout(x)
+        x = self.transformer(x, attn_mask=attn_mask)
+
+        # attention pooling: query i of a row attends to the tokens of image i of that row
+        Q = int(counts.max())
+        queries = self.attn_pool_queries[None, None, :].expand(B, Q, -1)
+        slot = torch.arange(Q, device=dev)
+        pool_mask = (slot[None, :, None] == image_ids[:, None, :]) & valid[:, None, :]
+        x = self.attn_pool(queries, context=x, attn_mask=pool_mask[:, None]) + queries
+        x = x.reshape(B * Q, -1)[(slot[None, :] < counts[:, None]).reshape(-1)]
+        return self.mlp_head(self.to_latent(x))
