@@ -204,12 +204,13 @@ def case_pool(B, N, D):
     return res
 
 
-def case_attention(B, N, H, psmem=0, lbo=1024, sbo=1024, time_it=False, skip_max=0):
+def case_attention(B, N, H, psmem=0, lbo=1024, sbo=1024, time_it=False, skip_max=0, pv_split=0):
     import torch
     from vit_pytorch_b200 import _lib
     L = _lib.lib()
     L.b200vit_debug_set(1, psmem)
     L.b200vit_debug_set(5, skip_max)
+    L.b200vit_debug_set(6, pv_split)
     L.b200vit_debug_set(2, lbo)
     L.b200vit_debug_set(3, sbo)
     torch.manual_seed(0)
@@ -293,6 +294,10 @@ CASES = {
     "attn_tmem_50": lambda: case_attention(3, 50, 4, psmem=0),
     "attn_tmem_big": lambda: case_attention(512, 197, 12, psmem=0, time_it=True),
     "attn_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True),
+    "attn_y_split_197": lambda: case_attention(4, 197, 12, pv_split=1),
+    "attn_y_split_64": lambda: case_attention(4, 64, 3, pv_split=1),
+    "attn_y_split_big": lambda: case_attention(512, 197, 12, time_it=True, pv_split=1),
+    "attn_y_split_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True, pv_split=1),
     "attn_x_skipmax_big": lambda: case_attention(512, 197, 12, psmem=0, time_it=True, skip_max=1),
     "attn_x_skipmax_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True, skip_max=1),
     "attn_1cta_197": lambda: case_attention(4, 197, 12, psmem=1),

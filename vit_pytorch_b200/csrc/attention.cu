@@ -31,6 +31,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
   int skip_max;           // experiment: skip the row-max pass (max := 0)
+  int pv_split;           // accumulate O = P V in two independent TMEM tiles (even / odd key steps), summed on read
 };
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
@@ -146,7 +147,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int ksteps = p.KP / 16;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
-          umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
+          // pv_split: two interleaved accumulation chains (the second tile sits 64 columns below the first)
+          const uint32_t d = (p.pv_split && (k & 1)) ? d_o - ATT_DH : d_o;
+          const uint32_t acc = p.pv_split ? (k >= 2) : (k != 0);
+          umma_ts(d, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, acc);
         }
         umma_commit(&o_full[t]);
       };
@@ -303,17 +307,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       uint32_t ob[32];  // 64 output columns as packed bf16 pairs
       if (warp_active) {
-        uint32_t r0[32];
-        tmem_ld_32x32b_x32(t_lane + O_COL, r0);
-        tmem_ld_wait();
+        uint32_t r0[32], r1[32];
+        const bool split = p.pv_split && p.KP >= 32;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          ob[j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
-        tmem_ld_32x32b_x32(t_lane + O_COL + 32, r0);
-        tmem_ld_wait();
+        for (int hcol = 0; hcol < 2; ++hcol) {
+          tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
+          if (split) tmem_ld_32x32b_x32(t_lane + O_COL - ATT_DH + 32 * hcol, r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          ob[16 + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(r0[2 * j]), bb = __uint_as_float(r0[2 * j + 1]);
+            if (split) {
+              a += __uint_as_float(r1[2 * j]);
+              bb += __uint_as_float(r1[2 * j + 1]);
+            }
+            ob[16 * hcol + j] = pack_bf16x2(a * inv, bb * inv);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -337,6 +347,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // debug / experiment knobs (b200vit_debug_set)
 static int g_attn_mode = 0;      // 0 auto (two CTAs / SM when possible), 1 force the one-CTA-per-SM variants
 static int g_attn_skip_max = 0;  // experiment only
+static int g_attn_pv_split = 0;
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 
@@ -368,6 +379,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
     case 5: g_attn_skip_max = value; return 0;
+    case 6: g_attn_pv_split = value; return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }
@@ -394,6 +406,8 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.skip_max = g_attn_skip_max;
+  // the second O tile occupies [O_COL-64, O_COL): it must not overlap P at [0, KP/2)
+  p.pv_split = (g_attn_pv_split && p.KP / 2 <= (occ2 || (N > 128 && p.KP <= 256) ? 256 : 512) - 2 * ATT_DH) ? 1 : 0;
   p.v_lbo = (unsigned)g_attn_v_lbo;
   p.v_sbo = (unsigned)g_attn_v_sbo;
 

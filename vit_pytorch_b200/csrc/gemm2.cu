@@ -145,6 +145,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tmem_relinquish_cg2();
   }
   tc_fence_before();
+  __syncthreads();     // CTA-local hand-off of the TMEM base address written by tcgen05.alloc
   cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
