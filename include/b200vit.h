@@ -102,6 +102,17 @@ int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, in
  */
 int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
 
+/*
+ * Variable-length attention over PACKED sequences (any length): tokens [cu_seqlens[s], cu_seqlens[s+1]) of
+ * qkv[total_tokens, 3*H*dh] attend only among themselves; out[total_tokens, H*dh].  This is the block-diagonal
+ * "same image" attention of NaViT (na_vit.py:335-337 mask + 161-166 SDPA) without padding or an O(L^2) mask, and the
+ * long-sequence (N > 512) path of ViT.  cu_seqlens_dev[num_seqs+1] and tile_prefix_dev[num_seqs+1] (number of 128-row
+ * query tiles before sequence s; tile_prefix[num_seqs] == total_tiles) are DEVICE int32 arrays built by the caller.
+ */
+int b200vit_attention_varlen(const void* qkv, void* out, const int32_t* cu_seqlens_dev, const int32_t* tile_prefix_dev,
+                             int num_seqs, int total_tokens, int total_tiles, int H, int dh, float scale,
+                             void* stream);
+
 /* Mean over tokens: x[B, N, D] fp32 -> out[B, D] fp32 (vit.py:135 pool == 'mean', simple_vit.py:117). */
 int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream);
 

@@ -247,7 +247,57 @@ def case_attention(B, N, H, psmem=0, lbo=1024, sbo=1024, time_it=False, skip_max
     return res
 
 
+def case_varlen(lengths, H, scale=0.125, time_it=False, seed=0):
+    import torch
+    from vit_pytorch_b200 import _lib
+    torch.manual_seed(seed)
+    dh = 64
+    I = H * dh
+    T = sum(lengths)
+    qkv = torch.randn(T, 3 * I, device="cuda").bfloat16()
+    out = torch.zeros(T, I, device="cuda", dtype=torch.bfloat16)
+    cu, tp, tiles = _lib.varlen_index(lengths, "cuda")
+    _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, scale)
+    torch.cuda.synchronize()
+    ref = torch.empty(T, I)
+    o = 0
+    for n in lengths:
+        q, k, v = qkv[o:o + n].float().cpu().view(n, 3, H, dh).permute(1, 2, 0, 3)
+        ref[o:o + n] = (((q @ k.transpose(-1, -2)) * scale).softmax(-1) @ v).permute(1, 0, 2).reshape(n, I)
+        o += n
+    res = {"bf16": _err(out.cpu(), ref)}
+    res["ok"] = res["bf16"]["within_tol"] > 0.995 and res["bf16"]["nan"] == 0
+    if not res["ok"]:
+        d = (out.float().cpu() - ref).abs()
+        res["err_by_token_head"] = d.mean(1)[:12].tolist()
+        res["sample_got"] = out[:2, :6].float().tolist()
+        res["sample_ref"] = ref[:2, :6].tolist()
+    if time_it:
+        for _ in range(3):
+            _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, scale)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(10):
+            _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, scale)
+        e1.record()
+        torch.cuda.synchronize()
+        res["ms"] = e0.elapsed_time(e1) / 10
+        res["gbps"] = (qkv.numel() + out.numel()) * 2 / res["ms"] / 1e6
+    return res
+
+
+def _navit_lengths():
+    import random
+    random.seed(0)
+    return [random.randrange(4, 33) * random.randrange(4, 33) for _ in range(256)]
+
+
 CASES = {
+    "varlen_one_block": lambda: case_varlen([64, 17, 128, 1, 100], 2),
+    "varlen_two_blocks": lambda: case_varlen([197, 130, 256, 129], 3),
+    "varlen_long": lambda: case_varlen([577, 1024, 300, 50], 2),
+    "varlen_vit_b16": lambda: case_varlen([197] * 512, 12, time_it=True),
+    "varlen_navit_cfg5": lambda: case_varlen(_navit_lengths(), 16, scale=1.0, time_it=True),
     "gemm_min": lambda: case_gemm(128, 256, 64),
     "gemm_k2": lambda: case_gemm(128, 256, 128),
     "gemm_k768": lambda: case_gemm(256, 512, 768),

@@ -26,7 +26,7 @@ SYMBOLS = [
     "b200vit_last_error", "b200vit_version", "b200vit_launch_count", "b200vit_reset_launch_count",
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
-    "b200vit_stats_parts",
+    "b200vit_stats_parts", "b200vit_attention_varlen",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     L.b200vit_debug_set.argtypes = [i32, i32]
     L.b200vit_attention.restype = i32
     L.b200vit_attention.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_attention_varlen.restype = i32
+    L.b200vit_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_mean_pool.restype = i32
     L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, vp]
     L.b200vit_cast_f32_bf16.restype = i32
@@ -260,6 +262,30 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, N: int, H: int, dh: 
     with _Timed("attention", B=B, N=N, H=H, bytes=(qkv.numel() + out.numel()) * 2, flops=4.0 * B * H * N * N * dh):
         rc = lib().b200vit_attention(_ptr(qkv), _ptr(out), B, N, H, dh, float(scale), _stream())
     _check(rc, "b200vit_attention")
+
+
+def varlen_index(lengths, device) -> tuple:
+    """(cu_seqlens, tile_prefix, total_tiles) device int32 tensors for b200vit_attention_varlen."""
+    cu, tp = [0], [0]
+    for n in lengths:
+        cu.append(cu[-1] + int(n))
+        tp.append(tp[-1] + (int(n) + 127) // 128)
+    return (torch.tensor(cu, dtype=torch.int32, device=device), torch.tensor(tp, dtype=torch.int32, device=device),
+            tp[-1])
+
+
+def attention_varlen(qkv: torch.Tensor, out: torch.Tensor, cu_seqlens: torch.Tensor, tile_prefix: torch.Tensor,
+                     total_tiles: int, H: int, dh: int, scale: float) -> None:
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out")
+    assert qkv.is_contiguous() and out.is_contiguous()
+    assert cu_seqlens.dtype == torch.int32 and tile_prefix.dtype == torch.int32 and cu_seqlens.is_cuda
+    T = qkv.shape[0]
+    S = cu_seqlens.numel() - 1
+    assert qkv.shape[1] == 3 * H * dh and out.shape == (T, H * dh) and tile_prefix.numel() == S + 1
+    with _Timed("attention_varlen", bytes=(qkv.numel() + out.numel()) * 2):
+        rc = lib().b200vit_attention_varlen(_ptr(qkv), _ptr(out), _ptr(cu_seqlens), _ptr(tile_prefix), S, T,
+                                            int(total_tiles), H, dh, float(scale), _stream())
+    _check(rc, "b200vit_attention_varlen")
 
 
 def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int) -> None:

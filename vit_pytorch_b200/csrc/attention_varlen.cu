@@ -1,0 +1,330 @@
+// Variable-length multi-head softmax attention over PACKED token sequences (cu_seqlens), any sequence length.
+//
+//   qkv[T, 3*H*64] bf16 (columns [q | k | v], head-major), sequences s = tokens [cu[s], cu[s+1])
+//   out[T, H*64]   bf16 :  out_s = softmax(q_s k_s^T * scale) v_s        -- tokens of different sequences never mix
+//
+// This is the block-diagonal ("same image id") attention of NaViT (reference na_vit.py:335-337,161-166) in its
+// mask-free varlen form, and the long-sequence path of ViT (N > 512).  Work unit = (sequence, head, 128-row query
+// tile); keys are walked in blocks of 128:
+//   phase 1 (only if the sequence has more than one key block): S_b = Q K_b^T for every block, softmax warps keep the
+//           running row max -- the FINAL max is known before any exponential is taken, so
+//   phase 2 needs no online rescaling: S_b again, P_b = exp2((S_b - max) * scale*log2e) as bf16 back into TMEM
+//           (aliasing S_b), O += P_b V_b accumulates in TMEM across blocks (tcgen05.mma accumulate flag), row sums in
+//           registers.  QK^T is computed twice; attention is exp/bandwidth bound, the tensor pipe has the headroom.
+// Keys >= n are masked to P = 0; rows >= n are computed on whatever follows in the buffer and never stored.
+// One softmax warpgroup per CTA, 192 TMEM columns (S|P at [0,128), O at [128,192)), 80 KB smem -> 2 CTAs per SM.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+namespace av {
+constexpr int DH = 64;
+constexpr int KB = 128;                      // keys per block
+constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
+constexpr int KV_STAGES = 2;
+constexpr int SMEM_DATA = TILE_BYTES * (1 + 2 * KV_STAGES);   // Q + 2 x (K, V)
+constexpr int NUM_BARS = 2 + 2 * KV_STAGES + 5;               // q_full q_empty kv_full[] kv_empty[] s_full s_free p_ready pv_done o_free
+constexpr int DYN_BYTES = SMEM_DATA + NUM_BARS * 8 + 16 + 1024;
+constexpr int TMEM_COLS = 256;
+constexpr int O_COL = 128;
+constexpr int THREADS = 6 * 32;
+}  // namespace av
+
+struct AttnVarlenParams {
+  const int* cu_seqlens;   // [S+1] device
+  const int* tile_prefix;  // [S+1] device: number of 128-row query tiles before sequence s
+  int num_seqs, H, I;
+  int units;               // total_tiles * H
+  float scale_log2e;
+  __nv_bfloat16* out;
+};
+
+__device__ __forceinline__ void av_locate(const AttnVarlenParams& p, int unit, int& seq, int& h, int& qt, int& row0,
+                                          int& n) {
+  const int tile = unit / p.H;  // heads of one query tile are neighbours: K/V of the sequence stay in L2
+  h = unit % p.H;
+  int lo = 0, hi = p.num_seqs;  // largest s with tile_prefix[s] <= tile
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+  }
+  seq = lo;
+  qt = tile - p.tile_prefix[seq];
+  row0 = p.cu_seqlens[seq];
+  n = p.cu_seqlens[seq + 1] - row0;
+}
+
+__global__ void __launch_bounds__(av::THREADS, 2)
+attention_varlen_kernel(const __grid_constant__ CUtensorMap tm, const AttnVarlenParams p) {
+  using namespace av;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + TILE_BYTES;  // stage st: K at sKV + st*2*TILE_BYTES, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_ready = s_free + 1;
+  uint64_t* pv_done = p_ready + 1;
+  uint64_t* o_free = pv_done + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int TMA_WARP = 4, MMA_WARP = 5;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
+    mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t units_done = 0, kv_count = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+        int seq, h, qt, row0, n;
+        av_locate(p, u, seq, h, qt, row0, n);
+        const int nb = (n + KB - 1) / KB;
+        mbar_wait(q_empty, (units_done & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(sQ, &tm, q_full, h * DH, row0 + qt * 128);
+        const int steps = (nb > 1 ? nb : 0) + nb;
+        for (int s = 0; s < steps; ++s, ++kv_count) {
+          const bool phase2 = s >= steps - nb;
+          const int kb = phase2 ? s - (steps - nb) : s;
+          const int st = kv_count % KV_STAGES;
+          mbar_wait(&kv_empty[st], ((kv_count / KV_STAGES) & 1) ^ 1);
+          uint8_t* k_dst = sKV + st * 2 * TILE_BYTES;
+          mbar_arrive_expect_tx(&kv_full[st], phase2 ? 2 * TILE_BYTES : TILE_BYTES);
+          tma_load_2d(k_dst, &tm, &kv_full[st], p.I + h * DH, row0 + kb * KB);
+          if (phase2) tma_load_2d(k_dst + TILE_BYTES, &tm, &kv_full[st], 2 * p.I + h * DH, row0 + kb * KB);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KB, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, DH, 0, 1);
+      uint32_t units_done = 0, kv_count = 0, n_sfree = 0, n_pready = 0, n_pv = 0;
+      bool wait_sfree = false, wait_pv = false;
+      const uint32_t sq = smem_u32(sQ);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+        int seq, h, qt, row0, n;
+        av_locate(p, u, seq, h, qt, row0, n);
+        const int nb = (n + KB - 1) / KB;
+        const int steps = (nb > 1 ? nb : 0) + nb;
+        mbar_wait(q_full, units_done & 1);
+        for (int s = 0; s < steps; ++s, ++kv_count) {
+          const bool phase2 = s >= steps - nb;
+          const int kb = phase2 ? s - (steps - nb) : s;
+          const int st = kv_count % KV_STAGES;
+          mbar_wait(&kv_full[st], (kv_count / KV_STAGES) & 1);
+          // the S|P region is free once the softmax warps have read S (phase 1) / the previous P V has completed
+          if (wait_sfree) {
+            mbar_wait(s_free, (n_sfree - 1) & 1);
+            wait_sfree = false;
+          }
+          if (wait_pv) {
+            mbar_wait(pv_done, (n_pv - 1) & 1);
+            wait_pv = false;
+          }
+          tc_fence_after();
+          const uint32_t sk = smem_u32(sKV + st * 2 * TILE_BYTES);
+          {
+            const uint64_t adesc = make_smem_desc_sw128(sq, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sk, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          }
+          umma_commit(s_full);
+          if (s == steps - 1) umma_commit(q_empty);  // last use of the Q tile
+          if (!phase2) {
+            umma_commit(&kv_empty[st]);
+            ++n_sfree;
+            wait_sfree = true;
+          } else {
+            if (kb == 0) {
+              mbar_wait(o_free, (units_done & 1) ^ 1);  // previous unit's O has been read
+            }
+            mbar_wait(p_ready, n_pready & 1);
+            ++n_pready;
+            tc_fence_after();
+            const uint32_t sv = sk + TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < KB / 16; ++k) {
+              const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
+              umma_ts(tmem_base + O_COL, tmem_base + k * 8, vdesc, idesc_pv, (kb | k) != 0);
+            }
+            umma_commit(&kv_empty[st]);
+            umma_commit(pv_done);
+            ++n_pv;
+            wait_pv = true;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup (thread == query row)
+    const int quad = warp & 3;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float c = p.scale_log2e;
+    uint32_t units_done = 0, n_sfull = 0, n_pv = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+      int seq, h, qt, row0, n;
+      av_locate(p, u, seq, h, qt, row0, n);
+      const int nb = (n + KB - 1) / KB;
+      const int qrow = qt * 128 + quad * 32 + lane;
+      float mx = -INFINITY;
+      auto block_max = [&](int kb) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < KB; c0 += 32) {
+          if (kb * KB + c0 >= n) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_lane + c0, r);
+          tmem_ld_wait();
+          const int lim = n - (kb * KB + c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      };
+      if (nb > 1) {
+        for (int kb = 0; kb < nb; ++kb, ++n_sfull) {
+          mbar_wait(s_full, n_sfull & 1);
+          tc_fence_after();
+          block_max(kb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
+        }
+      }
+      float sum = 0.f;
+      for (int kb = 0; kb < nb; ++kb, ++n_sfull) {
+        mbar_wait(s_full, n_sfull & 1);
+        tc_fence_after();
+        if (nb == 1) block_max(0);
+        const float mc = mx * c;
+#pragma unroll 1
+        for (int c0 = 0; c0 < KB; c0 += 32) {
+          uint32_t r[32];
+          uint32_t pk[16];
+          const int lim = n - (kb * KB + c0);  // number of valid keys in this chunk (may be <= 0)
+          if (lim > 0) {
+            tmem_ld_32x32b_x32(t_lane + c0, r);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float e0 = (j < lim) ? fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc)) : 0.f;
+            const float e1 = (j + 1 < lim) ? fast_ex2(fmaf(__uint_as_float(r[j + 1]), c, -mc)) : 0.f;
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32b_x16(t_lane + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        ++n_pv;
+      }
+      // epilogue: O / sum -> bf16 -> global
+      mbar_wait(pv_done, (n_pv - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      uint32_t ob[32];
+#pragma unroll
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      if (qrow < n) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + (size_t)(row0 + qrow) * p.I + h * DH);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_t* cu_seqlens_dev,
+                                        const int32_t* tile_prefix_dev, int num_seqs, int total_tokens, int total_tiles,
+                                        int H, int dh, float scale, void* stream) {
+  using namespace av;
+  B200_CHECK_ARG(qkv && out && cu_seqlens_dev && tile_prefix_dev, "attention_varlen: null pointer");
+  B200_CHECK_ARG(num_seqs > 0 && total_tokens > 0 && total_tiles > 0 && H > 0, "attention_varlen: bad shape");
+  B200_CHECK_ARG(dh == DH, "attention_varlen: dim_head=%d not supported by this build (only 64)", dh);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "attention_varlen: pointers must be 16-byte aligned");
+  AttnVarlenParams p{};
+  p.cu_seqlens = cu_seqlens_dev;
+  p.tile_prefix = tile_prefix_dev;
+  p.num_seqs = num_seqs;
+  p.H = H;
+  p.I = H * dh;
+  p.units = total_tiles * H;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  CUtensorMap tm;
+  const uint64_t dims[2] = {(uint64_t)3 * p.I, (uint64_t)total_tokens};
+  const uint64_t strides[1] = {(uint64_t)3 * p.I * 2};
+  const uint32_t box[2] = {64, 128};
+  int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DYN_BYTES));
+    attr_set = true;
+  }
+  const int slots = 2 * num_sms();
+  const int grid = p.units < slots ? p.units : slots;
+  attention_varlen_kernel<<<grid, THREADS, DYN_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
