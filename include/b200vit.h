@@ -113,6 +113,19 @@ int b200vit_attention_varlen(const void* qkv, void* out, const int32_t* cu_seqle
                              int num_seqs, int total_tokens, int total_tiles, int H, int dh, float scale,
                              void* stream);
 
+/*
+ * NaViT per-head q/k RMSNorm, in place on the packed qkv[T, 3*H*dh] buffer (q and k slices only):
+ *   v <- v / max(||v||, 1e-12) * sqrt(dh) * gamma[h, d]    (na_vit.py:93-101,149-150).  gamma_qk fp32 [2][H][dh].
+ */
+int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H, int dh, void* stream);
+
+/*
+ * NaViT attention pooling (na_vit.py:371-387): out[s, h*dh:(h+1)*dh] = softmax_j(qn_h . k_jh) v_jh over the tokens j of
+ * sequence s; kv[T, 2*H*dh] bf16 (k normalised, then v), qn[H*dh] fp32, cu_seqlens_dev[S+1] device int32, scale 1.
+ */
+int b200vit_attn_pool(const void* kv, const float* qn, const int32_t* cu_seqlens_dev, void* out, int S, int H, int dh,
+                      void* stream);
+
 /* Mean over tokens: x[B, N, D] fp32 -> out[B, D] fp32 (vit.py:135 pool == 'mean', simple_vit.py:117). */
 int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream);
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     "b200vit_last_error", "b200vit_version", "b200vit_launch_count", "b200vit_reset_launch_count",
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
-    "b200vit_stats_parts", "b200vit_attention_varlen",
+    "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
     L.b200vit_attention.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     L.b200vit_attention_varlen.restype = i32
     L.b200vit_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    L.b200vit_qk_rmsnorm.restype = i32
+    L.b200vit_qk_rmsnorm.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.b200vit_attn_pool.restype = i32
+    L.b200vit_attn_pool.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.b200vit_mean_pool.restype = i32
     L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, vp]
     L.b200vit_cast_f32_bf16.restype = i32
@@ -286,6 +290,26 @@ def attention_varlen(qkv: torch.Tensor, out: torch.Tensor, cu_seqlens: torch.Ten
         rc = lib().b200vit_attention_varlen(_ptr(qkv), _ptr(out), _ptr(cu_seqlens), _ptr(tile_prefix), S, T,
                                             int(total_tiles), H, dh, float(scale), _stream())
     _check(rc, "b200vit_attention_varlen")
+
+
+def qk_rmsnorm(qkv: torch.Tensor, gamma_qk: torch.Tensor, H: int, dh: int) -> None:
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(gamma_qk, torch.float32, "gamma_qk")
+    assert qkv.is_contiguous() and gamma_qk.is_contiguous() and gamma_qk.numel() == 2 * H * dh
+    T = qkv.shape[0]
+    assert qkv.shape[1] == 3 * H * dh
+    with _Timed("qk_rmsnorm", bytes=T * 2 * H * dh * 4):
+        rc = lib().b200vit_qk_rmsnorm(_ptr(qkv), _ptr(gamma_qk), T, H, dh, _stream())
+    _check(rc, "b200vit_qk_rmsnorm")
+
+
+def attn_pool(kv: torch.Tensor, qn: torch.Tensor, cu_seqlens: torch.Tensor, out: torch.Tensor, H: int, dh: int) -> None:
+    _chk(kv, torch.bfloat16, "kv"); _chk(qn, torch.float32, "qn"); _chk(out, torch.bfloat16, "out")
+    assert kv.is_contiguous() and qn.is_contiguous() and out.is_contiguous() and cu_seqlens.dtype == torch.int32
+    S = cu_seqlens.numel() - 1
+    assert kv.shape[1] == 2 * H * dh and out.shape == (S, H * dh) and qn.numel() == H * dh
+    with _Timed("attn_pool", bytes=kv.numel() * 2):
+        rc = lib().b200vit_attn_pool(_ptr(kv), _ptr(qn), _ptr(cu_seqlens), _ptr(out), S, H, dh, _stream())
+    _check(rc, "b200vit_attn_pool")
 
 
 def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int) -> None:

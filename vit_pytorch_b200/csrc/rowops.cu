@@ -419,3 +419,79 @@ extern "C" int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, 
   count_launch();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// NaViT: per-head q/k RMSNorm on the packed qkv buffer, in place (reference na_vit.py:93-101,149-150):
+//   v <- v / max(||v||_2, 1e-12) * sqrt(dh) * gamma[h, d]      for the q and k slices of every token and head.
+// gamma_qk: fp32 [2][H][dh] (q first), sqrt(dh) NOT folded in.  One warp per token, 2 elements per lane (dh = 64).
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+__global__ void __launch_bounds__(256)
+qk_rmsnorm_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ gamma_qk, int T, int H) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int I = H * 64;
+  __nv_bfloat16* row = qkv + t * 3 * I;
+  for (int hh = 0; hh < 2 * H; ++hh) {  // q heads then k heads: contiguous [2*I] at the start of the row
+    __nv_bfloat162* vp = reinterpret_cast<__nv_bfloat162*>(row + hh * 64) + lane;
+    const float2 v = __bfloat1622float2(*vp);
+    const float ss = warp_sum(v.x * v.x + v.y * v.y);
+    const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float2 g = *reinterpret_cast<const float2*>(gamma_qk + hh * 64 + 2 * lane);
+    *vp = __floats2bfloat162_rn(v.x * inv * g.x, v.y * inv * g.y);
+  }
+}
+
+// NaViT attention pooling (reference na_vit.py:371-387): one learned query per image attends to that image's tokens.
+//   kv[T, 2*H*64] bf16 (k already RMS-normalised, then v), qn[H*64] fp32 (normalised query), sequences by cu_seqlens;
+//   out[S, H*64] bf16 = softmax_j(qn_h . k_jh) v_jh   (scale 1).  One warp per (image, head), online softmax.
+__global__ void __launch_bounds__(128)
+attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__ qn, const int* __restrict__ cu,
+                 __nv_bfloat16* __restrict__ out, int S, int H) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= S * H) return;
+  const int s = w / H, h = w % H;
+  const int I = H * 64;
+  const float2 q = *reinterpret_cast<const float2*>(qn + h * 64 + 2 * lane);
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int j = cu[s]; j < cu[s + 1]; ++j) {
+    const __nv_bfloat16* r = kv + (long long)j * 2 * I + h * 64;
+    const float2 k = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r) + lane));
+    const float2 v = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r + I) + lane));
+    const float sc = warp_sum(q.x * k.x + q.y * k.y);
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn), pj = __expf(sc - mn);
+    l = l * corr + pj;
+    a0 = a0 * corr + pj * v.x;
+    a1 = a1 * corr + pj * v.y;
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  *(reinterpret_cast<__nv_bfloat162*>(out + (long long)s * I + h * 64) + lane) = __floats2bfloat162_rn(a0 * inv, a1 * inv);
+}
+
+}  // namespace b200
+
+extern "C" int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H, int dh, void* stream) {
+  B200_CHECK_ARG(qkv && gamma_qk && T > 0 && H > 0, "qk_rmsnorm: bad argument");
+  B200_CHECK_ARG(dh == 64, "qk_rmsnorm: dim_head=%d not supported by this build (only 64)", dh);
+  qk_rmsnorm_kernel<<<(T + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(qkv), gamma_qk, T, H);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200vit_attn_pool(const void* kv, const float* qn, const int32_t* cu_seqlens_dev, void* out, int S,
+                                 int H, int dh, void* stream) {
+  B200_CHECK_ARG(kv && qn && cu_seqlens_dev && out && S > 0 && H > 0, "attn_pool: bad argument");
+  B200_CHECK_ARG(dh == 64, "attn_pool: dim_head=%d not supported by this build (only 64)", dh);
+  attn_pool_kernel<<<(S * H + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(kv), qn, cu_seqlens_dev, reinterpret_cast<__nv_bfloat16*>(out), S, H);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}

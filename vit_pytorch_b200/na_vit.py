@@ -5,21 +5,26 @@ Same constructor keywords, parameter / buffer names, shapes and registration ord
 attention pooling with one learned query, bias-free head), same `forward(List[Tensor] | List[List[Tensor]],
 group_images=False, group_max_seq_len=2048) -> (num_images, num_classes)` and the same greedy packing helper.
 
-STATUS: this file is the interface mirror + PyTorch graph only.  The sm_100a path for it --
-a varlen (cu_seqlens) block-diagonal attention kernel with a key-block loop, the q/k RMSNorm prologue and the
-attention-pool kernel -- is the next row to build; `fused_reason()` says so and forward() always runs the graph below.
-
-Formulation: the reference pads packed rows and separates images with an O(B L^2) boolean mask.  Here every packed row
-is described by per-token image ids (the varlen description a kernel wants) and the mask is built once per call from
-them; arithmetic and outputs are identical (tests/test_navit.py against reference goldens).
+Two executions of the same arithmetic:
+  * PyTorch graph (CPU, fp32, training, autograd, hooks): packed rows + a boolean mask built from per-token image ids,
+    like the reference.
+  * fused sm_100a path (CUDA bf16, eval, no autograd): images never interact, so the packing and the O(B L^2) mask are
+    dropped altogether -- all tokens of all images form ONE padding-free [T, D] matrix described by cu_seqlens, the
+    encoder GEMMs run on it unchanged, attention is the varlen block-diagonal kernel (`b200vit_attention_varlen`, key
+    blocks of 128, any image size), q/k RMSNorm and the attention pooling are their own small kernels.  Patch
+    extraction ('c (h p1) (w p2) -> (h w) (c p1 p2)' per image) stays torch glue on the device: it is host-side packing
+    logic in the reference too (na_vit.py:288-325).
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Union
+from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
+
+from . import _lib
+from .engine import hooks_inside, why_not_fused
 
 
 def group_images_by_max_seq_len(images: Sequence[Tensor], patch_size: int,
@@ -160,8 +165,135 @@ class NaViT(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    # ------------------------------------------------------------------------------------------------------------
+    # fused sm_100a path
+    # ------------------------------------------------------------------------------------------------------------
     def fused_reason(self, batched_images=None) -> Optional[str]:
-        return "NaViT's sm_100a path (varlen block-diagonal attention, q/k RMSNorm, attention pooling) is not built yet"
+        """None if forward(batched_images) runs the hand-written kernels, else the reason for the PyTorch graph."""
+        if batched_images is None:
+            return "no input given"
+        first = batched_images[0] if torch.is_tensor(batched_images[0]) else batched_images[0][0]
+        attn0 = self.transformer.layers[0][0] if len(self.transformer.layers) else None
+        if attn0 is None:
+            return "depth == 0"
+        p_drop = max(self.dropout.p, attn0.dropout_p)
+        r = why_not_fused(list(self.parameters()), first, training=self.training, dropout_p=p_drop)
+        if r is None and self.training and self.calc_token_dropout is not None:
+            r = "token dropout is active"
+        if r is None and hooks_inside(self, skip=(self.to_latent,)):
+            r = "forward hooks registered inside the model"
+        if r is None and attn0.to_q.weight.shape[0] // attn0.heads != 64:
+            r = "dim_head != 64 (the attention kernels are built for 64)"
+        if r is None and (self.pos_embed_height.shape[1] % 8 or (self.channels * self.patch_size ** 2) % 8):
+            r = "dim / patch_dim not multiples of 8"
+        return r
+
+    def _prepared(self) -> Dict[str, Tensor]:
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_prep_key", None) == key:
+            return self._prep
+        f32 = lambda t: t.detach().float().contiguous()
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        t: Dict[str, Tensor] = {}
+        pe = self.to_patch_embedding
+        t["pe.ln1"], t["pe.w"], t["pe.b"], t["pe.ln2"] = f32(pe[0].gamma), bf(pe[1].weight), f32(pe[1].bias), f32(pe[2].gamma)
+        t["pos_h"], t["pos_w"] = f32(self.pos_embed_height), f32(self.pos_embed_width)
+
+        def attn_w(prefix: str, a: Attention) -> None:
+            t[prefix + "ln"] = f32(a.norm.gamma)
+            t[prefix + "qkv"] = bf(torch.cat([a.to_q.weight, a.to_kv.weight], dim=0))       # rows: q | k | v
+            t[prefix + "kv"] = bf(a.to_kv.weight)
+            t[prefix + "gqk"] = torch.stack([f32(a.q_norm.gamma).reshape(-1), f32(a.k_norm.gamma).reshape(-1)]).contiguous()
+            t[prefix + "out"] = bf(a.to_out[0].weight)
+
+        for i, (attn, ff) in enumerate(self.transformer.layers):
+            attn_w(f"{i}.a.", attn)
+            t[f"{i}.f.ln"] = f32(ff[0].gamma)
+            t[f"{i}.f.w1"], t[f"{i}.f.b1"] = bf(ff[1].weight), f32(ff[1].bias)
+            t[f"{i}.f.w2"], t[f"{i}.f.b2"] = bf(ff[4].weight), f32(ff[4].bias)
+        t["norm"] = f32(self.transformer.norm.gamma)
+        attn_w("pool.", self.attn_pool)
+        # the pooling query is the same for every image: LayerNorm -> to_q -> per-head RMSNorm, once per weight version
+        pool = self.attn_pool
+        qv = self.attn_pool_queries.detach().float()
+        qn = F.layer_norm(qv, qv.shape, pool.norm.gamma.detach().float(), None)
+        qh = (pool.to_q.weight.detach().float() @ qn).reshape(pool.heads, -1)
+        qh = F.normalize(qh, dim=-1) * pool.q_norm.scale * pool.q_norm.gamma.detach().float().reshape(pool.heads, -1)
+        t["pool.qn"] = qh.reshape(-1).contiguous()
+        t["pool.queries"] = qv.contiguous()
+        t["head.ln"], t["head.w"] = f32(self.mlp_head[0].gamma), bf(self.mlp_head[1].weight)
+        self._prep_key, self._prep = key, t
+        return t
+
+    @torch.no_grad()
+    def forward_fused(self, batched_images) -> Tensor:
+        if torch.is_tensor(batched_images[0]):
+            batched_images = [batched_images]
+        images = [im for row in batched_images for im in row]        # output order of the reference: row major
+        t = self._prepared()
+        dev = images[0].device
+        p, c = self.patch_size, self.channels
+        heads = self.attn_pool.heads
+        D = t["pos_h"].shape[1]
+        I = t["0.a.out"].shape[1]
+        # ---- host-side packing (torch glue): padding-free token matrix + positions + cu_seqlens
+        seqs, hs, ws, lengths = [], [], [], []
+        for img in images:
+            assert img.ndim == 3 and img.shape[0] == c
+            hh, ww = img.shape[-2:]
+            assert hh % p == 0 and ww % p == 0, f'height and width {(hh, ww)} of images must be divisible by patch size {p}'
+            gh, gw = hh // p, ww // p
+            seqs.append(img.reshape(c, gh, p, gw, p).permute(1, 3, 0, 2, 4).reshape(gh * gw, c * p * p))
+            hs.append(torch.arange(gh, device=dev).repeat_interleave(gw))
+            ws.append(torch.arange(gw, device=dev).repeat(gh))
+            lengths.append(gh * gw)
+        patches = torch.cat(seqs).float()
+        h_idx, w_idx = torch.cat(hs), torch.cat(ws)
+        T, S = patches.shape[0], len(images)
+        cu, tile_prefix, total_tiles = _lib.varlen_index(lengths, dev)
+        bf16 = dict(device=dev, dtype=torch.bfloat16)
+        # ---- patch embedding: LN(no bias) -> Linear -> LN(no bias) -> + pos_h + pos_w      (na_vit.py:350-359)
+        a0 = torch.empty(T, patches.shape[1], **bf16)
+        _lib.layernorm(patches, t["pe.ln1"], None, out_bf16=a0)
+        y = torch.empty(T, D, device=dev, dtype=torch.float32)
+        _lib.gemm(a0, t["pe.w"], out_f32=y, bias=t["pe.b"])
+        x = torch.empty_like(y)
+        _lib.layernorm(y, t["pe.ln2"], None, out_f32=x)
+        x += t["pos_h"][h_idx]
+        x += t["pos_w"][w_idx]
+        # ---- encoder layers on the packed [T, D] matrix                                     (na_vit.py:183-193)
+        xn = torch.empty(T, D, **bf16)
+        qkv = torch.empty(T, 3 * I, **bf16)
+        o = torch.empty(T, I, **bf16)
+        hbuf = torch.empty(T, t["0.f.w1"].shape[0], **bf16)
+        for i in range(len(self.transformer.layers)):
+            _lib.layernorm(x, t[f"{i}.a.ln"], None, out_bf16=xn)
+            _lib.gemm(xn, t[f"{i}.a.qkv"], out_bf16=qkv)
+            _lib.qk_rmsnorm(qkv, t[f"{i}.a.gqk"], heads, 64)
+            _lib.attention_varlen(qkv, o, cu, tile_prefix, total_tiles, heads, 64, 1.0)
+            _lib.gemm(o, t[f"{i}.a.out"], out_f32=x, resid=x)
+            _lib.layernorm(x, t[f"{i}.f.ln"], None, out_bf16=xn)
+            _lib.gemm(xn, t[f"{i}.f.w1"], out_bf16=hbuf, bias=t[f"{i}.f.b1"], gelu=True)
+            _lib.gemm(hbuf, t[f"{i}.f.w2"], out_f32=x, bias=t[f"{i}.f.b2"], resid=x)
+        _lib.layernorm(x, t["norm"], None, out_bf16=xn)
+        # ---- attention pooling: one query per image over that image's (un-normalised-again) tokens (na_vit.py:371-387)
+        kv = torch.empty(T, 2 * I, **bf16)
+        _lib.gemm(xn, t["pool.kv"], out_bf16=kv)
+        kq = torch.empty(T, 3 * I, **bf16)          # qk_rmsnorm works on a [q | k | v] buffer: place k, v at 1/3, 2/3
+        kq[:, I:] = kv
+        kq[:, :I] = 0
+        _lib.qk_rmsnorm(kq, t["pool.gqk"], heads, 64)
+        pooled = torch.empty(S, I, **bf16)
+        _lib.attn_pool(kq[:, I:].contiguous(), t["pool.qn"], cu, pooled, heads, 64)
+        z = t["pool.queries"][None, :].expand(S, -1).contiguous()
+        _lib.gemm(pooled, t["pool.out"], out_f32=z, resid=z)                      # + queries
+        zl = torch.empty(S, D, **bf16)
+        _lib.layernorm(z, t["head.ln"], None, out_bf16=zl)
+        zl = self.to_latent(zl)
+        logits = torch.empty(S, t["head.w"].shape[0], **bf16)
+        _lib.gemm(zl, t["head.w"], out_bf16=logits)
+        return logits
 
     # ------------------------------------------------------------------------------------------------------------
     def _tokenise_row(self, images: Sequence[Tensor], training_dropout: bool):
@@ -188,6 +320,14 @@ class NaViT(nn.Module):
 
     def forward(self, batched_images: Union[List[Tensor], List[List[Tensor]]], group_images: bool = False,
                 group_max_seq_len: int = 2048) -> Tensor:
+        if self.fused_reason(batched_images) is None:
+            # grouping only decides which images share a padded row; the padding-free path does not need it, and the
+            # output order (input order) is the same either way
+            return self.forward_fused(batched_images)
+        return self.forward_eager(batched_images, group_images, group_max_seq_len)
+
+    def forward_eager(self, batched_images: Union[List[Tensor], List[List[Tensor]]], group_images: bool = False,
+                      group_max_seq_len: int = 2048) -> Tensor:
         dev = self.device
         training_dropout = self.calc_token_dropout is not None and self.training
         if group_images:
