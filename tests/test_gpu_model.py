@@ -150,6 +150,23 @@ def test_large_configs_against_oracle(name, kwargs, floor_max, floor_frac):
     assert mx < floor_max and frac > floor_frac, (mx, mean, frac)
 
 
+def test_long_sequence_uses_key_block_attention():
+    """384x384 input (N = 577 > 512): the encoder switches to the key-block (varlen) attention kernel."""
+    kwargs = dict(image_size=384, patch_size=16, num_classes=10, dim=256, depth=2, heads=4, mlp_dim=512)
+    torch.manual_seed(0)
+    m = ViT(**kwargs).eval().bfloat16()
+    torch.manual_seed(1)
+    img = torch.randn(2, 3, 384, 384).bfloat16()
+    ref = O.vit_forward(O.upcast(m.state_dict()), kwargs, img.float())
+    m = m.to(DEV)
+    with torch.inference_mode():
+        assert m.fused_reason(img.to(DEV)) is None
+        out = m(img.to(DEV))
+    mx, mean, frac = stats(out, ref)
+    print(f"ViT 384^2 (N=577) vs fp32 oracle: max {mx:.5f} mean {mean:.5f} within_tol {frac:.4f}")
+    assert mx < 2e-2 and frac > 0.85
+
+
 @pytest.mark.parametrize("mode", ["exact", "fold"])
 def test_full_batch_properties_b512(mode, monkeypatch):
     monkeypatch.setenv("B200VIT_LN_MODE", mode)

@@ -127,8 +127,8 @@ class TransformerEngine:
                 return "attention without output projection (heads == 1 and dim_head == dim)"
             if attn.dim % 8 or ff.hidden_dim % 8:
                 return "dim / mlp_dim not multiples of 8"
-        if N > 512:
-            return f"sequence length {N} > 512 (online-softmax attention not built yet)"
+        if N > 16384:
+            return f"sequence length {N} > 16384"
         return None
 
     # -------------------------------------------------------------------------------------------- weights
@@ -185,6 +185,18 @@ class TransformerEngine:
         return self.ws
 
     # -------------------------------------------------------------------------------------------- execution
+    def _attention(self, ws: Dict[str, torch.Tensor], B: int, N: int, attn) -> None:
+        """Single-pass kernel for N <= 512 keys, the key-block (varlen) kernel beyond."""
+        if N <= 512:
+            _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+            return
+        key = (B, N, ws["qkv"].device)
+        if getattr(self, "_vl_key", None) != key:
+            self._vl = _lib.varlen_index([N] * B, ws["qkv"].device)
+            self._vl_key = key
+        cu, tp, tiles = self._vl
+        _lib.attention_varlen(ws["qkv"], ws["o"], cu, tp, tiles, attn.heads, attn.dim_head, attn.scale)
+
     def run_blocks(self, x: torch.Tensor, B: int, N: int, primed: bool = False) -> None:
         """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm).
 
@@ -200,7 +212,7 @@ class TransformerEngine:
             for i, (attn, ff) in enumerate(self._layers()):
                 _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
                           ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"])
-                _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+                self._attention(ws, B, N, attn)
                 _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
                           stats_out=sb)
                 _lib.gemm(xb, t[f"{i}.fc1.wg"], out_bf16=ws["h"], bias=t[f"{i}.fc1.t"], gelu=True, ln_sums=sb,
@@ -211,7 +223,7 @@ class TransformerEngine:
         for i, (attn, ff) in enumerate(self._layers()):
             _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"])
             _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
-            _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+            self._attention(ws, B, N, attn)
             _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, bias=t[f"{i}.out.b"], resid=x)
             _lib.layernorm(x, t[f"{i}.ln2.w"], t[f"{i}.ln2.b"], out_bf16=ws["xn"])
             _lib.gemm(ws["xn"], t[f"{i}.fc1.w"], out_bf16=ws["h"], bias=t[f"{i}.fc1.b"], gelu=True)
