@@ -429,18 +429,39 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256)
 qk_rmsnorm_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ gamma_qk, int T, int H) {
+  // one warp per token; 8 lanes per head (8 bf16 = 16 B each), so four heads are normalised per step with a
+  // 3-step butterfly inside each 8-lane group
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
   const int I = H * 64;
   __nv_bfloat16* row = qkv + t * 3 * I;
-  for (int hh = 0; hh < 2 * H; ++hh) {  // q heads then k heads: contiguous [2*I] at the start of the row
-    __nv_bfloat162* vp = reinterpret_cast<__nv_bfloat162*>(row + hh * 64) + lane;
-    const float2 v = __bfloat1622float2(*vp);
-    const float ss = warp_sum(v.x * v.x + v.y * v.y);
+  const int sub = lane & 7;
+  for (int base = 0; base < 2 * H; base += 4) {  // q heads then k heads: the first 2*I columns of the row
+    const int hh = base + (lane >> 3);
+    const bool act = hh < 2 * H;               // (2H not a multiple of 4: the tail groups only join the shuffles)
+    uint4* vp = reinterpret_cast<uint4*>(row + (act ? hh : 0) * 64) + sub;
+    uint4 raw = *vp;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
+    float2 f[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[i] = __bfloat1622float2(h2[i]);
+      ss = fmaf(f[i].x, f[i].x, fmaf(f[i].y, f[i].y, ss));
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
-    const float2 g = *reinterpret_cast<const float2*>(gamma_qk + hh * 64 + 2 * lane);
-    *vp = __floats2bfloat162_rn(v.x * inv * g.x, v.y * inv * g.y);
+    if (!act) continue;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma_qk + hh * 64 + 8 * sub);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma_qk + hh * 64 + 8 * sub + 4);
+    h2[0] = __floats2bfloat162_rn(f[0].x * inv * g0.x, f[0].y * inv * g0.y);
+    h2[1] = __floats2bfloat162_rn(f[1].x * inv * g0.z, f[1].y * inv * g0.w);
+    h2[2] = __floats2bfloat162_rn(f[2].x * inv * g1.x, f[2].y * inv * g1.y);
+    h2[3] = __floats2bfloat162_rn(f[3].x * inv * g1.z, f[3].y * inv * g1.w);
+    *vp = raw;
   }
 }
 
