@@ -114,6 +114,16 @@ int b200vit_attention_varlen(const void* qkv, void* out, const int32_t* cu_seqle
                              void* stream);
 
 /*
+ * NaViT patch extraction over a LIST of images of different resolutions + LayerNorm(patch_dim) without bias, one launch:
+ *   out[cu[s] + h*gw_s + w, (c*p + p1)*p + p2] = LN_patch(img_s[c, h*p + p1, w*p + p2]) * gamma      (na_vit.py:300,350)
+ * img_ptrs_dev[S]: device array of the (contiguous bf16 [C, H_s, W_s]) images' addresses; dims_dev[S][2] = (H_s, W_s);
+ * cu_seqlens_dev[S+1] token offsets; row_prefix_dev[S+1] = number of patch rows before image s.
+ */
+int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int32_t* dims_dev, const int32_t* cu_seqlens_dev,
+                               const int32_t* row_prefix_dev, const float* gamma, void* out_bf16, int64_t ldo, int S,
+                               int total_rows, int max_w, int C, int p, float eps, void* stream);
+
+/*
  * NaViT per-head q/k RMSNorm, in place on the packed qkv[T, 3*H*dh] buffer (q and k slices only):
  *   v <- v / max(||v||, 1e-12) * sqrt(dh) * gamma[h, d]    (na_vit.py:93-101,149-150).  gamma_qk fp32 [2][H][dh].
  */

@@ -27,6 +27,7 @@ SYMBOLS = [
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
+    "b200vit_patchify_varlen_ln",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -73,6 +74,8 @@ def lib() -> C.CDLL:
     L.b200vit_attention.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     L.b200vit_attention_varlen.restype = i32
     L.b200vit_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    L.b200vit_patchify_varlen_ln.restype = i32
+    L.b200vit_patchify_varlen_ln.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_qk_rmsnorm.restype = i32
     L.b200vit_qk_rmsnorm.argtypes = [vp, vp, i32, i32, i32, vp]
     L.b200vit_attn_pool.restype = i32
@@ -290,6 +293,29 @@ def attention_varlen(qkv: torch.Tensor, out: torch.Tensor, cu_seqlens: torch.Ten
         rc = lib().b200vit_attention_varlen(_ptr(qkv), _ptr(out), _ptr(cu_seqlens), _ptr(tile_prefix), S, T,
                                             int(total_tiles), H, dh, float(scale), _stream())
     _check(rc, "b200vit_attention_varlen")
+
+
+def patchify_varlen_ln(images, gamma: torch.Tensor, out_bf16: torch.Tensor, cu_seqlens: torch.Tensor, p: int,
+                       eps: float = 1e-5) -> None:
+    """images: list of contiguous CUDA bf16 [C, H, W] tensors (kept alive by the caller until the stream has run)."""
+    _chk(gamma, torch.float32, "gamma"); _chk(out_bf16, torch.bfloat16, "out")
+    dev = out_bf16.device
+    C = images[0].shape[0]
+    ptrs, dims, rows = [], [], [0]
+    for im in images:
+        assert im.is_cuda and im.dtype == torch.bfloat16 and im.is_contiguous() and im.shape[0] == C
+        ptrs.append(im.data_ptr())
+        dims += [im.shape[1], im.shape[2]]
+        rows.append(rows[-1] + im.shape[1] // p)
+    t_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+    t_dims = torch.tensor(dims, dtype=torch.int32, device=dev)
+    t_rows = torch.tensor(rows, dtype=torch.int32, device=dev)
+    max_w = max(im.shape[2] for im in images)
+    with _Timed("patchify_varlen_ln", bytes=out_bf16.numel() * 4):
+        rc = lib().b200vit_patchify_varlen_ln(_ptr(t_ptrs), _ptr(t_dims), _ptr(cu_seqlens), _ptr(t_rows), _ptr(gamma),
+                                              _ptr(out_bf16), out_bf16.stride(0), len(images), rows[-1], max_w, C, p,
+                                              float(eps), _stream())
+    _check(rc, "b200vit_patchify_varlen_ln")
 
 
 def qk_rmsnorm(qkv: torch.Tensor, gamma_qk: torch.Tensor, H: int, dh: int) -> None:

@@ -516,3 +516,91 @@ extern "C" int b200vit_attn_pool(const void* kv, const float* qn, const int32_t*
   count_launch();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// NaViT patch extraction for a LIST of images of different sizes + LayerNorm(patch_dim, no bias), one launch:
+//   out[cu[s] + h*gw_s + w, (c*p + p1)*p + p2] = LN_over_patch(img_s[c, h*p + p1, w*p + p2]) * gamma
+// (reference na_vit.py:300 'c (h p1) (w p2) -> (h w) (c p1 p2)' + to_patch_embedding[0], na_vit.py:224-228,350).
+// One CTA per patch row of one image (persistent): the C x p x W_s pixel slab is staged in shared memory with
+// coalesced loads, then each warp normalises whole patches.  img_ptrs: device array of the images' data pointers.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+__global__ void __launch_bounds__(256)
+patchify_varlen_ln_kernel(const long long* __restrict__ img_ptrs, const int* __restrict__ dims,
+                          const int* __restrict__ cu, const int* __restrict__ row_prefix,
+                          const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out, long long ldo, int S, int C,
+                          int p, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [C][p][W]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_rows = row_prefix[S];
+  const int pd = C * p * p;
+  for (int r = blockIdx.x; r < total_rows; r += gridDim.x) {
+    int lo = 0, hi = S;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_prefix[mid] <= r) lo = mid; else hi = mid;
+    }
+    const int s = lo, h = r - row_prefix[s];
+    const int H = dims[2 * s], W = dims[2 * s + 1];
+    const int gw = W / p;
+    const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(img_ptrs[s]);
+    __syncthreads();  // previous slab fully consumed
+    const int row_elems = p * W;
+    for (int i = threadIdx.x; i < C * row_elems; i += blockDim.x) {
+      const int c = i / row_elems, rr = i % row_elems;
+      slab[i] = img[((long long)c * H + (long long)h * p) * W + rr];
+    }
+    __syncthreads();
+    for (int w = warp; w < gw; w += 8) {
+      // element e = (c*p + p1)*p + p2  <->  slab[(c*p + p1)*W + w*p + p2]
+      float sum = 0.f;
+      for (int e = lane; e < pd; e += 32) sum += __bfloat162float(slab[(e / p) * W + w * p + (e % p)]);
+      const float mean = warp_sum(sum) / (float)pd;
+      float q = 0.f;
+      for (int e = lane; e < pd; e += 32) {
+        const float d = __bfloat162float(slab[(e / p) * W + w * p + (e % p)]) - mean;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)pd + eps);
+      __nv_bfloat16* orow = out + ((long long)cu[s] + (long long)h * gw + w) * ldo;
+      for (int e = lane; e < (int)ldo; e += 32) {
+        float y = 0.f;
+        if (e < pd) y = (__bfloat162float(slab[(e / p) * W + w * p + (e % p)]) - mean) * rstd * gamma[e];
+        orow[e] = __float2bfloat16_rn(y);
+      }
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int32_t* dims_dev,
+                                          const int32_t* cu_seqlens_dev, const int32_t* row_prefix_dev,
+                                          const float* gamma, void* out_bf16, int64_t ldo, int S, int total_rows,
+                                          int max_w, int C, int p, float eps, void* stream) {
+  B200_CHECK_ARG(img_ptrs_dev && dims_dev && cu_seqlens_dev && row_prefix_dev && gamma && out_bf16,
+                 "patchify_varlen_ln: null pointer");
+  B200_CHECK_ARG(S > 0 && total_rows > 0 && C > 0 && p > 0 && max_w >= p, "patchify_varlen_ln: bad shape");
+  B200_CHECK_ARG(ldo >= (int64_t)C * p * p, "patchify_varlen_ln: ldo too small");
+  const size_t smem = (size_t)C * p * max_w * 2;
+  B200_CHECK_ARG(smem <= 200 * 1024, "patchify_varlen_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+    smem_set = smem;
+  }
+  int per_sm = (int)(200 * 1024 / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int grid = b200::num_sms() * per_sm;
+  if (grid > total_rows) grid = total_rows;
+  b200::patchify_varlen_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(img_ptrs_dev), dims_dev, cu_seqlens_dev, row_prefix_dev, gamma,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, S, C, p, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}

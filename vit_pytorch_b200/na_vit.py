@@ -237,25 +237,29 @@ class NaViT(nn.Module):
         heads = self.attn_pool.heads
         D = t["pos_h"].shape[1]
         I = t["0.a.out"].shape[1]
-        # ---- host-side packing (torch glue): padding-free token matrix + positions + cu_seqlens
-        seqs, hs, ws, lengths = [], [], [], []
+        # ---- host-side bookkeeping only: per-image token counts -> cu_seqlens; patch pixels are gathered on the GPU
+        lengths, gws = [], []
         for img in images:
             assert img.ndim == 3 and img.shape[0] == c
             hh, ww = img.shape[-2:]
             assert hh % p == 0 and ww % p == 0, f'height and width {(hh, ww)} of images must be divisible by patch size {p}'
-            gh, gw = hh // p, ww // p
-            seqs.append(img.reshape(c, gh, p, gw, p).permute(1, 3, 0, 2, 4).reshape(gh * gw, c * p * p))
-            hs.append(torch.arange(gh, device=dev).repeat_interleave(gw))
-            ws.append(torch.arange(gw, device=dev).repeat(gh))
-            lengths.append(gh * gw)
-        patches = torch.cat(seqs).float()
-        h_idx, w_idx = torch.cat(hs), torch.cat(ws)
-        T, S = patches.shape[0], len(images)
+            lengths.append((hh // p) * (ww // p))
+            gws.append(ww // p)
+        images = [im.contiguous() for im in images]
+        S = len(images)
+        T = sum(lengths)
         cu, tile_prefix, total_tiles = _lib.varlen_index(lengths, dev)
+        # token -> (row, column) in its image's patch grid, vectorised (factorised positional tables, na_vit.py:354-359)
+        lens_t = torch.tensor(lengths, device=dev)
+        img_of = torch.repeat_interleave(torch.arange(S, device=dev), lens_t)
+        local = torch.arange(T, device=dev) - cu[:-1].long()[img_of]
+        gw_t = torch.tensor(gws, device=dev)[img_of]
+        h_idx, w_idx = local // gw_t, local % gw_t
         bf16 = dict(device=dev, dtype=torch.bfloat16)
-        # ---- patch embedding: LN(no bias) -> Linear -> LN(no bias) -> + pos_h + pos_w      (na_vit.py:350-359)
-        a0 = torch.empty(T, patches.shape[1], **bf16)
-        _lib.layernorm(patches, t["pe.ln1"], None, out_bf16=a0)
+        # ---- patch embedding: patchify + LN(no bias) -> Linear -> LN(no bias) -> + pos_h + pos_w  (na_vit.py:300,350-359)
+        pd = c * p * p
+        a0 = torch.empty(T, pd, **bf16)
+        _lib.patchify_varlen_ln(images, t["pe.ln1"], a0, cu, p)
         y = torch.empty(T, D, device=dev, dtype=torch.float32)
         _lib.gemm(a0, t["pe.w"], out_f32=y, bias=t["pe.b"])
         x = torch.empty_like(y)
