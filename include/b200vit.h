@@ -144,7 +144,8 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
 
 /* Experiment knobs for kernel bring-up (not part of the drop-in surface).
  * key 1: attention variant (0 = auto, 1 = force one CTA per SM); key 2/3: V descriptor LBO / SBO bytes;
- * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies). */
+ * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies);
+ * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation). */
 int b200vit_debug_set(int key, int value);
 
 #ifdef __cplusplus
