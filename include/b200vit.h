@@ -147,6 +147,8 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
  * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies);
  * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation). */
 int b200vit_debug_set(int key, int value);
+/* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention */
+void b200vit_debug_set_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
   int skip_max;           // experiment: skip the row-max pass (max := 0)
+  long long* trace;       // timing experiment: [iteration][16] globaltimer stamps of CTA 0 (NULL = off)
   int pv_split;           // accumulate O = P V in two independent TMEM tiles (even / odd key steps), summed on read
 };
 
@@ -119,6 +120,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);  // B = V is MN-major
+      auto stamp = [&](int it, int slot) {
+        if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + slot] = (long long)globaltimer_ns();
+      };
       // S_t(it) = Q_t K^T into region t  (waits until the epilogue of unit it-1 has drained the region)
       auto issue_s = [&](int it, int t) {
         const int s = it % STAGES;
@@ -136,6 +140,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         }
         umma_commit(&s_full[t]);
+        if (t == 0) stamp(it, 2);
       };
       // O_t(it) = P_t V  (A = P from TMEM, B = V as MN-major smem operand: 16 keys = two 8-row groups = 2048 B)
       auto issue_pv = [&](int it, int t) {
@@ -143,6 +148,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t sv = smem_u32(smem + s * stage_bytes) + kv_bytes;
         mbar_wait(&p_ready[t], it & 1);
         tc_fence_after();
+        if (t == 0) stamp(it, 3);
         const uint32_t d_o = tmem_base + t * REGION + O_COL;
         const int ksteps = p.KP / 16;
         for (int k = 0; k < ksteps; ++k) {
@@ -153,10 +159,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ts(d, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, acc);
         }
         umma_commit(&o_full[t]);
+        if (t == 0) stamp(it, 4);
       };
       auto wait_full = [&](int it) {
+        stamp(it, 0);
         mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);
         tc_fence_after();
+        stamp(it, 1);
       };
       const int n_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       if (NWG == 2 && STAGES == 2) {
@@ -204,8 +213,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // warps whose 32 query rows all lie beyond N skip the arithmetic but keep the barrier protocol in lockstep
       const bool warp_active = (round * NWG + t) * 128 + quad * 32 < p.N;
 
+      const bool tr = p.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && it < 64;
+      if (tr) p.trace[it * 16 + 8] = (long long)globaltimer_ns();
       mbar_wait(&s_full[t], up);
       tc_fence_after();
+      if (tr) p.trace[it * 16 + 9] = (long long)globaltimer_ns();
       float sum = 1.f;
       if (warp_active) {
         // Columns [0, 32*nfull) need no key mask; the rest (< 48 columns) is handled 16 at a time with the mask.
@@ -300,11 +312,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[t]);
+      if (tr) p.trace[it * 16 + 10] = (long long)globaltimer_ns();
 
       // epilogue: O / sum -> bf16 -> global
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
+      if (tr) p.trace[it * 16 + 11] = (long long)globaltimer_ns();
       uint32_t ob[32];  // 64 output columns as packed bf16 pairs
       if (warp_active) {
         uint32_t r0[32], r1[32];
@@ -333,6 +347,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
+      if (tr) p.trace[it * 16 + 12] = (long long)globaltimer_ns();
     }
   }
 
@@ -348,6 +363,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 static int g_attn_mode = 0;      // 0 auto (two CTAs / SM when possible), 1 force the one-CTA-per-SM variants
 static int g_attn_skip_max = 0;  // experiment only
 static int g_attn_pv_split = 0;
+static long long* g_attn_trace = nullptr;
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 
@@ -371,6 +387,8 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, con
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" void b200vit_debug_set_trace(void* dev_buf) { g_attn_trace = reinterpret_cast<long long*>(dev_buf); }
 
 extern "C" int b200vit_debug_set(int key, int value) {
   switch (key) {
@@ -405,6 +423,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.units = B * H * p.rounds;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.trace = g_attn_trace;
   p.skip_max = g_attn_skip_max;
   // the second O tile occupies [O_COL-64, O_COL): it must not overlap P at [0, KP/2)
   p.pv_split = (g_attn_pv_split && p.KP / 2 <= (occ2 || (N > 128 && p.KP <= 256) ? 256 : 512) - 2 * ATT_DH) ? 1 : 0;

@@ -309,11 +309,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ----------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (FFMA2 on sm_100: two IEEE fp32 FMAs per issue slot) -- the GEMM epilogues are bound by
+// FMA-pipe issue, so everything element-wise runs on pairs
+// ----------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_get(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // GELU in its exact-erf definition (nn.GELU() default, reference vit.py:21), evaluated as x * Phi(x) with
 //   Phi(x) = 1 / (1 + exp(-x * (c0 + c1 x^2 + c2 x^4 + c3 x^6))),   x clamped to [-6, 6] inside Phi,
 // the odd polynomial being a minimax fit of logit(Phi) (max |gelu_fit - gelu_erf| = 1.2e-5 over all x, checked in
 // float32 including the approximate ex2/rcp; i.e. < 1/100 of a bf16 ulp of the output wherever |y| >= 0.25).
-// 5 FMA-pipe + 2 MUFU + 2 ALU instructions, branch free -- the FC1 epilogue is issue-bound, so this matters.
+// 5 FMA-pipe + 2 MUFU + 2 ALU instructions, branch free.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
   const float x2 = xc * xc;
@@ -323,6 +352,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, x2, -2.301647186279297f);
   const float e = fast_ex2(p * xc);            // exp(-u)
   return x * fast_rcp(1.0f + e);
+}
+// the same on a pair (identical per-lane arithmetic, half the FMA-pipe instructions)
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+  const float ac = fminf(fmaxf(a, -6.0f), 6.0f), bc = fminf(fmaxf(b, -6.0f), 6.0f);
+  const f32x2 xc = f2_make(ac, bc);
+  const f32x2 x2 = f2_mul(xc, xc);
+  f32x2 p = f2_fma(f2_make(2.4836384909576736e-05f, 2.4836384909576736e-05f), x2,
+                   f2_make(7.3606101796031e-04f, 7.3606101796031e-04f));
+  p = f2_fma(p, x2, f2_make(-1.0598272830247879e-01f, -1.0598272830247879e-01f));
+  p = f2_fma(p, x2, f2_make(-2.301647186279297f, -2.301647186279297f));
+  float u0, u1;
+  f2_get(f2_mul(p, xc), u0, u1);
+  const f32x2 d = f2_add(f2_make(fast_ex2(u0), fast_ex2(u1)), f2_make(1.0f, 1.0f));
+  float d0, d1;
+  f2_get(d, d0, d1);
+  f2_get(f2_mul(f2_make(a, b), f2_make(fast_rcp(d0), fast_rcp(d1))), a, b);
 }
 
 }  // namespace b200

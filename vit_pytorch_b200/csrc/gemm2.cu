@@ -61,32 +61,35 @@ struct Gemm2Params {
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
 };
 
-// LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32)
+// LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32), on fp32 PAIRS (FFMA2):
+//   LN-fold + bias:  y = acc * rstd + (bias - rstd*mu * s)        2 packed FMAs per pair
 template <int W>
 __device__ __forceinline__ void epilogue_math(float (&v)[W], int col0, int flags, float mu, float rstd,
                                               const Gemm2Params& p) {
-  if (flags & B200VIT_EPI_LNFOLD) {
+  if (flags & (B200VIT_EPI_LNFOLD | B200VIT_EPI_BIAS)) {
+    const bool fold = (flags & B200VIT_EPI_LNFOLD) != 0;
+    const bool has_bias = (flags & B200VIT_EPI_BIAS) != 0;
+    const float k = -rstd * mu;
+    const f32x2 k2 = f2_make(k, k), r2 = f2_make(fold ? rstd : 1.0f, fold ? rstd : 1.0f);
 #pragma unroll
     for (int j = 0; j < W; j += 4) {
-      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + j < p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
-      v[j] = rstd * fmaf(-mu, s4.x, v[j]);
-      v[j + 1] = rstd * fmaf(-mu, s4.y, v[j + 1]);
-      v[j + 2] = rstd * fmaf(-mu, s4.z, v[j + 2]);
-      v[j + 3] = rstd * fmaf(-mu, s4.w, v[j + 3]);
-    }
-  }
-  if (flags & B200VIT_EPI_BIAS) {
-#pragma unroll
-    for (int j = 0; j < W; j += 4) {
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col0 + j < p.N) {
+        if (fold) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
+        if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      }
+      f32x2 c01 = f2_make(b4.x, b4.y), c23 = f2_make(b4.z, b4.w);
+      if (fold) {
+        c01 = f2_fma(k2, f2_make(s4.x, s4.y), c01);
+        c23 = f2_fma(k2, f2_make(s4.z, s4.w), c23);
+      }
+      f2_get(f2_fma(f2_make(v[j], v[j + 1]), r2, c01), v[j], v[j + 1]);
+      f2_get(f2_fma(f2_make(v[j + 2], v[j + 3]), r2, c23), v[j + 2], v[j + 3]);
     }
   }
   if (flags & B200VIT_EPI_GELU) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < W; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
 }
 
