@@ -200,18 +200,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
             const bool full8 = (col + 8 <= p.N);
             if (full8 && vec_ok) {
-              if (flags & B200VIT_EPI_LNFOLD) {
-                const float4 s0 = *reinterpret_cast<const float4*>(p.col_s + col);
-                const float4 s1 = *reinterpret_cast<const float4*>(p.col_s + col + 4);
-                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              if (flags & (B200VIT_EPI_LNFOLD | B200VIT_EPI_BIAS)) {
+                // y = acc * rstd + (bias - rstd*mu * s): the same two FMAs as the CTA-pair kernel, so both kernels
+                // give bit-identical results (batch-size invariance across the kernel switch at M = 1024)
+                const bool fold = (flags & B200VIT_EPI_LNFOLD) != 0;
+                float cv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (flags & B200VIT_EPI_BIAS) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                  cv[0] = b0.x; cv[1] = b0.y; cv[2] = b0.z; cv[3] = b0.w;
+                  cv[4] = b1.x; cv[5] = b1.y; cv[6] = b1.z; cv[7] = b1.w;
+                }
+                if (fold) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(p.col_s + col);
+                  const float4 s1 = *reinterpret_cast<const float4*>(p.col_s + col + 4);
+                  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                  const float k = -rstd * mu;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = rstd * fmaf(-mu, sv[i], v[i]);
-              }
-              if (flags & B200VIT_EPI_BIAS) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                  for (int i = 0; i < 8; ++i) cv[i] = fmaf(k, sv[i], cv[i]);
+                }
+                const float rs = fold ? rstd : 1.0f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], rs, cv[i]);
               }
               if (flags & B200VIT_EPI_GELU) {
 #pragma unroll
@@ -250,8 +260,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int i = 0; i < 8 && col + i < p.N; ++i) {
                 float x = v[i];
                 const int cc = col + i;
-                if (flags & B200VIT_EPI_LNFOLD) x = rstd * fmaf(-mu, p.col_s[cc], x);
-                if (flags & B200VIT_EPI_BIAS) x += p.bias[cc];
+                if (flags & (B200VIT_EPI_LNFOLD | B200VIT_EPI_BIAS)) {
+                  float cvs = (flags & B200VIT_EPI_BIAS) ? p.bias[cc] : 0.f;
+                  if (flags & B200VIT_EPI_LNFOLD) cvs = fmaf(-rstd * mu, p.col_s[cc], cvs);
+                  x = fmaf(x, (flags & B200VIT_EPI_LNFOLD) ? rstd : 1.0f, cvs);
+                }
                 if (flags & B200VIT_EPI_GELU) x = gelu_erf(x);
                 if (flags & B200VIT_EPI_RESIDUAL) x += p.resid[(size_t)row * p.ldo + cc];
                 if (p.out_f32) p.out_f32[(size_t)row * p.ldo + cc] = x;

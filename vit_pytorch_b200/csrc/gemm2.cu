@@ -93,6 +93,37 @@ __device__ __forceinline__ void epilogue_math(float (&v)[W], int col0, int flags
   }
 }
 
+// per-row LayerNorm statistics from up to 8 partial (sum, sum^2) pairs: all loads are issued before the first add
+// (independent L2 round trips instead of a dependent chain), summation order is fixed => deterministic
+__device__ __forceinline__ void load_row_stats(const Gemm2Params& p, int row, float& mu, float& rstd) {
+  float2 part[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    part[i] = (i < p.ln_parts) ? __ldg(reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i)))
+                               : make_float2(0.f, 0.f);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s1 += part[i].x;
+    s2 += part[i].y;
+  }
+  for (int i = 8; i < p.ln_parts; ++i) {  // (more than 8 partials: N of the producer > 1024)
+    const float2 ss = __ldg(reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i)));
+    s1 += ss.x;
+    s2 += ss.y;
+  }
+  mu = s1 * p.ln_inv_dim;
+  rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+}
+// pull the bias / column-sum slices a warp is about to use into L1 (non-blocking)
+__device__ __forceinline__ void prefetch_cols(const Gemm2Params& p, int flags, int col_base, int ncols, int lane) {
+  const int c = col_base + lane * 32;  // one 128-byte line per lane
+  if (lane * 32 < ncols && c < p.N) {
+    if (flags & B200VIT_EPI_BIAS) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + c));
+    if (flags & B200VIT_EPI_LNFOLD) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.col_s + c));
+  }
+}
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::Cfg<MODE>::NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -289,23 +320,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     if constexpr (MODE == MODE_BF16) {
       // ============ bf16 output: 64 columns per warp = one staging box per tile, x16 loads double buffered
+      int stats_m_pair = -1;
+      float stats_mu = 0.f, stats_rstd = 1.f;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_pair = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         const int row0 = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32;
         const int row = row0 + lane;
-        float mu = 0.f, rstd = 1.f;
-        if ((flags & B200VIT_EPI_LNFOLD) && row < p.M) {
-          float s1 = 0.f, s2 = 0.f;
-          for (int i = 0; i < p.ln_parts; ++i) {
-            const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
-            s1 += ss.x;
-            s2 += ss.y;
-          }
-          mu = s1 * p.ln_inv_dim;
-          rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
-        }
         const int col_base = n_blk * BLOCK_N + col_off;
+        prefetch_cols(p, flags, col_base, COLS_PER_WARP, lane);
+        float mu = 0.f, rstd = 1.f;
+        if (flags & B200VIT_EPI_LNFOLD) {
+          if (row < p.M) {
+            if (m_pair != stats_m_pair) {
+              load_row_stats(p, row, stats_mu, stats_rstd);
+              stats_m_pair = m_pair;
+            }
+            mu = stats_mu;
+            rstd = stats_rstd;
+          }
+          // the statistics of this thread's row in the NEXT tile of this cluster: into L1 while this tile is processed
+          const int ntile = tile + num_clusters;
+          if (ntile < num_tiles) {
+            const int nrow = (ntile / p.num_n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32 + lane;
+            if (nrow < p.M)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ln_sums + 2 * ((size_t)nrow * p.ln_parts)));
+          }
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + col_off;
@@ -368,16 +409,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row = m_pair * (2 * BLOCK_M) + rank * BLOCK_M + quad * 32 + lane;
         const bool row_ok = row < p.M;
         float mu = 0.f, rstd = 1.f;
-        if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
-          float s1 = 0.f, s2 = 0.f;
-          for (int i = 0; i < p.ln_parts; ++i) {
-            const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
-            s1 += ss.x;
-            s2 += ss.y;
-          }
-          mu = s1 * p.ln_inv_dim;
-          rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
-        }
+        prefetch_cols(p, flags, n_blk * BLOCK_N + col_off, COLS_PER_WARP, lane);
+        if ((flags & B200VIT_EPI_LNFOLD) && row_ok) load_row_stats(p, row, mu, rstd);
         if (DUAL) st_sum = st_sq = 0.f;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
