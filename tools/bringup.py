@@ -296,6 +296,9 @@ CASES = {
     "varlen_one_block": lambda: case_varlen([64, 17, 128, 1, 100], 2),
     "varlen_two_blocks": lambda: case_varlen([197, 130, 256, 129], 3),
     "varlen_long": lambda: case_varlen([577, 1024, 300, 50], 2),
+    "cmp257_single": lambda: case_attention(128, 257, 16, time_it=True),
+    "cmp257_varlen": lambda: case_varlen([257] * 128, 16, time_it=True),
+    "cmp577_varlen": lambda: case_varlen([577] * 64, 12, time_it=True),
     "varlen_vit_b16": lambda: case_varlen([197] * 512, 12, time_it=True),
     "varlen_navit_cfg5": lambda: case_varlen(_navit_lengths(), 16, scale=1.0, time_it=True),
     "gemm_min": lambda: case_gemm(128, 256, 64),
