@@ -296,6 +296,12 @@ CASES = {
     "varlen_one_block": lambda: case_varlen([64, 17, 128, 1, 100], 2),
     "varlen_two_blocks": lambda: case_varlen([197, 130, 256, 129], 3),
     "varlen_long": lambda: case_varlen([577, 1024, 300, 50], 2),
+    "split2_197": lambda: case_attention(4, 197, 12, psmem=2),
+    "split3_197": lambda: case_attention(4, 197, 12, psmem=3),
+    "split2_129": lambda: case_attention(3, 129, 2, psmem=2),
+    "split3_256": lambda: case_attention(2, 256, 2, psmem=3),
+    "split2_big": lambda: case_attention(512, 197, 12, psmem=2, time_it=True),
+    "split3_big": lambda: case_attention(512, 197, 12, psmem=3, time_it=True),
     "cmp257_single": lambda: case_attention(128, 257, 16, time_it=True),
     "cmp257_varlen": lambda: case_varlen([257] * 128, 16, time_it=True),
     "cmp577_varlen": lambda: case_varlen([577] * 64, 12, time_it=True),

@@ -360,7 +360,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // debug / experiment knobs (b200vit_debug_set)
-static int g_attn_mode = 0;      // 0 auto (two CTAs / SM when possible), 1 force the one-CTA-per-SM variants
+static int g_attn_mode = 0;      // 0 auto, 1 force the one-CTA-per-SM variants, 2 / 3 the 8-warps-per-tile variants
+int launch_attention_split_variant(int variant, const void* qkv, void* out, int B, int N, int H, float scale,
+                                   cudaStream_t stream);
 static int g_attn_skip_max = 0;  // experiment only
 static int g_attn_pv_split = 0;
 static long long* g_attn_trace = nullptr;
@@ -409,6 +411,8 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   B200_CHECK_ARG(N <= 512, "attention: N=%d > 512 needs the (unbuilt) online-softmax path", N);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "attention: pointers must be 16-byte aligned");
+  if ((g_attn_mode == 2 || g_attn_mode == 3) && N > 128 && N <= 256)
+    return launch_attention_split_variant(g_attn_mode, qkv, out, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
   AttnParams p{};
   p.B = B; p.N = N; p.H = H;
   p.I = H * dh;
