@@ -127,7 +127,11 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int ksteps = p.KP / 16;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
-            umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
+            // P of column half 0 is packed at [0, split/2), P of half 1 at [split, split + (KP-split)/2): each half
+            // overwrites only score columns its own warp has already consumed
+            const int key0 = 16 * k;
+            const int a_col = key0 < p.split_col ? (key0 >> 1) : p.split_col + ((key0 - p.split_col) >> 1);
+            umma_ts(d_o, tmem_base + t * REGION + a_col, vdesc, idesc_pv, k != 0);
           }
           umma_commit(&o_full[t]);
         }
@@ -197,7 +201,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           s1 += e1;
           pk[j >> 1] = pack_bf16x2(e0, e1);
         }
-        tmem_st_32x32b_x16(t_lane + (c0 >> 1), pk);
+        tmem_st_32x32b_x16(t_lane + c_lo + ((c0 - c_lo) >> 1), pk);
       }
       for (c0 = c_tail; c0 < c_hi; c0 += 16) {
         uint32_t r16[16];
@@ -212,7 +216,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           s1 += e1;
           pk8[j >> 1] = pack_bf16x2(e0, e1);
         }
-        tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk8);
+        tmem_st_32x32b_x8(t_lane + c_lo + ((c0 - c_lo) >> 1), pk8);
       }
       tmem_st_wait();
       *my_sum = s0 + s1;
