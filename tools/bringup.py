@@ -204,13 +204,14 @@ def case_pool(B, N, D):
     return res
 
 
-def case_attention(B, N, H, psmem=0, lbo=1024, sbo=1024, time_it=False, skip_max=0, pv_split=0):
+def case_attention(B, N, H, psmem=0, lbo=1024, sbo=1024, time_it=False, skip_max=0, pv_split=0, exp_emul=0):
     import torch
     from vit_pytorch_b200 import _lib
     L = _lib.lib()
     L.b200vit_debug_set(1, psmem)
     L.b200vit_debug_set(5, skip_max)
     L.b200vit_debug_set(6, pv_split)
+    L.b200vit_debug_set(7, exp_emul)
     L.b200vit_debug_set(2, lbo)
     L.b200vit_debug_set(3, sbo)
     torch.manual_seed(0)
@@ -296,6 +297,14 @@ CASES = {
     "varlen_one_block": lambda: case_varlen([64, 17, 128, 1, 100], 2),
     "varlen_two_blocks": lambda: case_varlen([197, 130, 256, 129], 3),
     "varlen_long": lambda: case_varlen([577, 1024, 300, 50], 2),
+    "emul8_197": lambda: case_attention(4, 197, 12, exp_emul=8),
+    "emul16_197": lambda: case_attention(4, 197, 12, exp_emul=16),
+    "emul16_64": lambda: case_attention(4, 64, 3, exp_emul=16),
+    "emul0_big": lambda: case_attention(512, 197, 12, time_it=True, exp_emul=0),
+    "emul8_big": lambda: case_attention(512, 197, 12, time_it=True, exp_emul=8),
+    "emul16_big": lambda: case_attention(512, 197, 12, time_it=True, exp_emul=16),
+    "emul16_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True, exp_emul=16),
+    "emul8_1cta_big": lambda: case_attention(512, 197, 12, psmem=1, time_it=True, exp_emul=8),
     "split2_197": lambda: case_attention(4, 197, 12, psmem=2),
     "split3_197": lambda: case_attention(4, 197, 12, psmem=3),
     "split2_129": lambda: case_attention(3, 129, 2, psmem=2),

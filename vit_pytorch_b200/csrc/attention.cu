@@ -31,6 +31,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
   int skip_max;           // experiment: skip the row-max pass (max := 0)
+  int exp_emul;           // 0 / 8 / 16 of every 32 exponentials on the FMA pipe instead of MUFU
   long long* trace;       // timing experiment: [iteration][16] globaltimer stamps of CTA 0 (NULL = off)
   int pv_split;           // accumulate O = P V in two independent TMEM tiles (even / odd key steps), summed on read
 };
@@ -261,20 +262,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
         // ---------------- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#define ATT_EXP32(R, C0)                                                                      \
+// E = number of leading elements of each 32-column chunk whose exponential is computed on the FMA pipe (exp2_emul2)
+#define ATT_EXP32_E(R, C0, E)                                                                 \
   {                                                                                           \
     uint32_t pk[16];                                                                          \
+    const f32x2 c2v = f2_make(c, c), nmc2v = f2_make(-mc, -mc);                               \
     _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                       \
-      const float e0 = fast_ex2(fmaf(__uint_as_float(R[j]), c, -mc));                         \
-      const float e1 = fast_ex2(fmaf(__uint_as_float(R[j + 1]), c, -mc));                     \
-      const float e2 = fast_ex2(fmaf(__uint_as_float(R[j + 2]), c, -mc));                     \
-      const float e3 = fast_ex2(fmaf(__uint_as_float(R[j + 3]), c, -mc));                     \
+      const f32x2 xa = f2_fma(f2_make(__uint_as_float(R[j]), __uint_as_float(R[j + 1])), c2v, nmc2v);     \
+      const f32x2 xb = f2_fma(f2_make(__uint_as_float(R[j + 2]), __uint_as_float(R[j + 3])), c2v, nmc2v); \
+      float e0, e1, e2, e3;                                                                   \
+      if (j < (E)) {                                                                          \
+        exp2_emul2(xa, e0, e1);                                                               \
+        exp2_emul2(xb, e2, e3);                                                               \
+      } else {                                                                                \
+        float x0, x1, x2, x3;                                                                 \
+        f2_get(xa, x0, x1);                                                                   \
+        f2_get(xb, x2, x3);                                                                   \
+        e0 = fast_ex2(x0); e1 = fast_ex2(x1); e2 = fast_ex2(x2); e3 = fast_ex2(x3);           \
+      }                                                                                       \
       s0 += e0; s1 += e1; s2 += e2; s3 += e3;                                                 \
       pk[j >> 1] = pack_bf16x2(e0, e1);                                                       \
       pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);                                                 \
     }                                                                                         \
     tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
   }
+#define ATT_EXP32(R, C0)                                     \
+  if (p.exp_emul == 8) ATT_EXP32_E(R, C0, 8)                 \
+  else if (p.exp_emul == 16) ATT_EXP32_E(R, C0, 16)          \
+  else ATT_EXP32_E(R, C0, 0)
         ci = 0;
         if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
@@ -306,6 +321,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
 #undef ATT_MAX32
 #undef ATT_EXP32
+#undef ATT_EXP32_E
         sum = (s0 + s1) + (s2 + s3);
         tmem_st_wait();
       }
@@ -365,6 +381,7 @@ int launch_attention_split_variant(int variant, const void* qkv, void* out, int 
                                    cudaStream_t stream);
 static int g_attn_skip_max = 0;  // experiment only
 static int g_attn_pv_split = 0;
+static int g_attn_exp_emul = 0;
 static long long* g_attn_trace = nullptr;
 static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
 static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
@@ -400,6 +417,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 4: gemm_force_version(value); return 0;
     case 5: g_attn_skip_max = value; return 0;
     case 6: g_attn_pv_split = value; return 0;
+    case 7: g_attn_exp_emul = value; return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }
@@ -429,6 +447,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.trace = g_attn_trace;
   p.skip_max = g_attn_skip_max;
+  p.exp_emul = g_attn_exp_emul;
   // the second O tile occupies [O_COL-64, O_COL): it must not overlap P at [0, KP/2)
   p.pv_split = (g_attn_pv_split && p.KP / 2 <= (occ2 || (N > 128 && p.KP <= 256) ? 256 : 512) - 2 * ATT_DH) ? 1 : 0;
   p.v_lbo = (unsigned)g_attn_v_lbo;
