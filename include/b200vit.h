@@ -143,7 +143,8 @@ int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* str
 int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
 
 /* Experiment knobs for kernel bring-up (not part of the drop-in surface).
- * key 1: attention variant (0 = auto, 1 = force one CTA per SM); key 2/3: V descriptor LBO / SBO bytes;
+ * key 1: attention variant (0 = auto, 1 = one CTA per SM, 2 / 3 = 8 softmax warps per score tile); key 2/3: V descriptor
+ * LBO / SBO bytes; key 7: FMA-pipe exp2 for 0 / 8 / 16 of every 32 softmax exponentials;
  * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies);
  * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation). */
 int b200vit_debug_set(int key, int value);
