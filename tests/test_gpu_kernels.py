@@ -348,6 +348,26 @@ def test_attention(B, N, H):
     assert (out.float().cpu() - ref).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("knob,value", [(1, 1), (1, 2), (1, 3), (7, 8), (7, 16), (6, 1)])
+def test_attention_experimental_variants_stay_correct(knob, value):
+    """One-CTA-per-SM, 8-warps-per-tile, FMA-pipe exp2 and split-PV variants (b200vit_debug_set) are not the default
+    but must keep producing the same attention."""
+    L = _lib.lib()
+    torch.manual_seed(7)
+    B, N, H, dh = 3, 197, 4, 64
+    qkv = torch.randn(B * N, 3 * H * dh, device=DEV).bfloat16()
+    ref_out = torch.zeros(B * N, H * dh, device=DEV, dtype=torch.bfloat16)
+    _lib.attention(qkv, ref_out, B, N, H, dh, dh ** -0.5)
+    out = torch.zeros_like(ref_out)
+    L.b200vit_debug_set(knob, value)
+    try:
+        _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+        torch.cuda.synchronize()
+    finally:
+        L.b200vit_debug_set(knob, 0)
+    assert within(out, ref_out.float(), rtol=2e-2, atol=2e-3) > 0.999
+
+
 def test_attention_large_logits_are_stable():
     torch.manual_seed(9)
     B, N, H, dh = 2, 197, 2, 64
