@@ -17,12 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def _err(got, ref):
+def _err(got, ref, atol=1e-3):
     import torch
     got = got.float()
     ref = ref.float()
     d = (got - ref).abs()
-    tol = 1e-3 + 1e-2 * ref.abs()
+    tol = atol + 1e-2 * ref.abs()
     return {
         "max_abs": float(d.max()),
         "mean_abs": float(d.mean()),
@@ -83,7 +83,8 @@ def case_gemm(M, N, K, bias=False, gelu=False, resid=False, f32=False, both=Fals
         res["f32"] = _err(out_f32_first if inplace else out_f32, ref)
     if stats:
         rb = ref.bfloat16().float()
-        res["stats_sum"] = _err(st.sum(1)[:, 0], rb.sum(1))
+        # a row sum of N terms cancels: its error scales with sqrt(N) * |term|, not with the (possibly tiny) sum
+        res["stats_sum"] = _err(st.sum(1)[:, 0], rb.sum(1), atol=1e-3 * float(rb.abs().max()) * N ** 0.5)
         res["stats_sq"] = _err(st.sum(1)[:, 1], (rb * rb).sum(1))
     # timing
     if M * N * K > 1e9:

@@ -41,10 +41,16 @@ __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { ret
 // TMEM_COLS = 512: one CTA per SM (NWG regions of 512/NWG columns).  TMEM_COLS = 256 (NWG = 1, one K/V/Q stage):
 // TWO independent CTAs per SM, each with one softmax warpgroup -- while one CTA waits for its MMAs or loads, the
 // other one's softmax keeps the MUFU / issue slots busy.
-template <int NWG, int STAGES, int TMEM_COLS>
+// DBG = true compiles the experiment knobs of b200vit_debug_set (trace stamps, skip_max, pv_split, exp_emul) in; the
+// production instantiation (DBG = false) carries none of them.
+template <int NWG, int STAGES, int TMEM_COLS, bool DBG>
 __global__ void __launch_bounds__((4 * NWG + 2) * 32, TMEM_COLS == 256 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttnParams p) {
+  const int k_skip_max = DBG ? p.skip_max : 0;
+  const int k_exp_emul = DBG ? p.exp_emul : 0;
+  const int k_pv_split = DBG ? p.pv_split : 0;
+  long long* const k_trace = DBG ? p.trace : nullptr;
   constexpr int REGION = TMEM_COLS / NWG;
   constexpr int O_COL = REGION - ATT_DH;
   constexpr int NUM_SOFTMAX_WARPS = 4 * NWG;
@@ -122,7 +128,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);  // B = V is MN-major
       auto stamp = [&](int it, int slot) {
-        if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + slot] = (long long)globaltimer_ns();
+        if (k_trace && blockIdx.x == 0 && it < 64) k_trace[it * 16 + slot] = (long long)globaltimer_ns();
       };
       // S_t(it) = Q_t K^T into region t  (waits until the epilogue of unit it-1 has drained the region)
       auto issue_s = [&](int it, int t) {
@@ -155,8 +161,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
           // pv_split: two interleaved accumulation chains (the second tile sits 64 columns below the first)
-          const uint32_t d = (p.pv_split && (k & 1)) ? d_o - ATT_DH : d_o;
-          const uint32_t acc = p.pv_split ? (k >= 2) : (k != 0);
+          const uint32_t d = (k_pv_split && (k & 1)) ? d_o - ATT_DH : d_o;
+          const uint32_t acc = k_pv_split ? (k >= 2) : (k != 0);
           umma_ts(d, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, acc);
         }
         umma_commit(&o_full[t]);
@@ -214,11 +220,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // warps whose 32 query rows all lie beyond N skip the arithmetic but keep the barrier protocol in lockstep
       const bool warp_active = (round * NWG + t) * 128 + quad * 32 < p.N;
 
-      const bool tr = p.trace && blockIdx.x == 0 && warp == 0 && lane == 0 && it < 64;
-      if (tr) p.trace[it * 16 + 8] = (long long)globaltimer_ns();
+      const bool tr = k_trace && blockIdx.x == 0 && warp == 0 && lane == 0 && it < 64;
+      if (tr) k_trace[it * 16 + 8] = (long long)globaltimer_ns();
       mbar_wait(&s_full[t], up);
       tc_fence_after();
-      if (tr) p.trace[it * 16 + 9] = (long long)globaltimer_ns();
+      if (tr) k_trace[it * 16 + 9] = (long long)globaltimer_ns();
       float sum = 1.f;
       if (warp_active) {
         // Columns [0, 32*nfull) need no key mask; the rest (< 48 columns) is handled 16 at a time with the mask.
@@ -234,11 +240,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     m3 = fmaxf(m3, __uint_as_float(R[j + 3]));                          \
   }
         int ci = 0;
-        if (p.skip_max) {
+        if (k_skip_max) {
           m0 = m1 = m2 = m3 = 0.f;
           ci = 1 << 20;
         }
-        if (!p.skip_max && nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
+        if (!k_skip_max && nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
           tmem_ld_wait();
           tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
@@ -251,7 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_wait();
           ATT_MAX32(ra)
         }
-        for (int c0 = nfull * 32; c0 < p.KP && !p.skip_max; c0 += 16) {
+        for (int c0 = nfull * 32; c0 < p.KP && !k_skip_max; c0 += 16) {
           uint32_t r16[16];
           tmem_ld_32x32b_x16(t_lane + c0, r16);
           tmem_ld_wait();
@@ -286,10 +292,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }                                                                                         \
     tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
   }
-#define ATT_EXP32(R, C0)                                     \
-  if (p.exp_emul == 8) ATT_EXP32_E(R, C0, 8)                 \
-  else if (p.exp_emul == 16) ATT_EXP32_E(R, C0, 16)          \
-  else ATT_EXP32_E(R, C0, 0)
+#define ATT_EXP32_PLAIN(R, C0)                                                                \
+  {                                                                                           \
+    uint32_t pk[16];                                                                          \
+    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                       \
+      const float e0 = fast_ex2(fmaf(__uint_as_float(R[j]), c, -mc));                         \
+      const float e1 = fast_ex2(fmaf(__uint_as_float(R[j + 1]), c, -mc));                     \
+      const float e2 = fast_ex2(fmaf(__uint_as_float(R[j + 2]), c, -mc));                     \
+      const float e3 = fast_ex2(fmaf(__uint_as_float(R[j + 3]), c, -mc));                     \
+      s0 += e0; s1 += e1; s2 += e2; s3 += e3;                                                 \
+      pk[j >> 1] = pack_bf16x2(e0, e1);                                                       \
+      pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);                                                 \
+    }                                                                                         \
+    tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
+  }
+#define ATT_EXP32(R, C0)                                            \
+  if (DBG && k_exp_emul == 8) ATT_EXP32_E(R, C0, 8)                 \
+  else if (DBG && k_exp_emul == 16) ATT_EXP32_E(R, C0, 16)          \
+  else ATT_EXP32_PLAIN(R, C0)
         ci = 0;
         if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
@@ -322,23 +342,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #undef ATT_MAX32
 #undef ATT_EXP32
 #undef ATT_EXP32_E
+#undef ATT_EXP32_PLAIN
         sum = (s0 + s1) + (s2 + s3);
         tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[t]);
-      if (tr) p.trace[it * 16 + 10] = (long long)globaltimer_ns();
+      if (tr) k_trace[it * 16 + 10] = (long long)globaltimer_ns();
 
       // epilogue: O / sum -> bf16 -> global
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
-      if (tr) p.trace[it * 16 + 11] = (long long)globaltimer_ns();
+      if (tr) k_trace[it * 16 + 11] = (long long)globaltimer_ns();
       uint32_t ob[32];  // 64 output columns as packed bf16 pairs
       if (warp_active) {
         uint32_t r0[32], r1[32];
-        const bool split = p.pv_split && p.KP >= 32;
+        const bool split = k_pv_split && p.KP >= 32;
 #pragma unroll
         for (int hcol = 0; hcol < 2; ++hcol) {
           tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
@@ -363,7 +384,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
-      if (tr) p.trace[it * 16 + 12] = (long long)globaltimer_ns();
+      if (tr) k_trace[it * 16 + 12] = (long long)globaltimer_ns();
     }
   }
 
@@ -389,11 +410,12 @@ static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
 template <int NWG, int STAGES, int TMEM_COLS = 512>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, size_t smem_bytes,
                             cudaStream_t stream) {
-  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS>;
-  static size_t smem_set = 0;
-  if (smem_bytes > smem_set) {
+  const bool dbg = p.trace || p.skip_max || p.exp_emul || p.pv_split;
+  auto kern = dbg ? attention_kernel<NWG, STAGES, TMEM_COLS, true> : attention_kernel<NWG, STAGES, TMEM_COLS, false>;
+  static size_t smem_set[2] = {0, 0};
+  if (smem_bytes > smem_set[dbg]) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    smem_set = smem_bytes;
+    smem_set[dbg] = smem_bytes;
   }
   const int slots = num_sms() * (TMEM_COLS == 256 ? 2 : 1);
   const int grid = p.units < slots ? p.units : slots;
@@ -418,6 +440,8 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 5: g_attn_skip_max = value; return 0;
     case 6: g_attn_pv_split = value; return 0;
     case 7: g_attn_exp_emul = value; return 0;
+    case 8: gemm2_set_feed_skip(value); return 0;
+    case 9: gemm2_set_l2_prefetch(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }

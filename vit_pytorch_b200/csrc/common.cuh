@@ -82,6 +82,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
+// pull one box of a tensor into L2 (no shared memory, no completion signal): hides the HBM part of the load latency
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -361,35 +367,37 @@ __device__ __forceinline__ void exp2_emul2(f32x2 x, float& e0, float& e1) {
 }
 
 // GELU in its exact-erf definition (nn.GELU() default, reference vit.py:21), evaluated as x * Phi(x) with
-//   Phi(x) = 1 / (1 + exp(-x * (c0 + c1 x^2 + c2 x^4 + c3 x^6))),   x clamped to [-6, 6] inside Phi,
+//   Phi(x) = 1 / (1 + exp(-x * (c0 + c1 x^2 + c2 x^4 + c3 x^6))),   x^2 clamped to 36 inside the polynomial,
 // the odd polynomial being a minimax fit of logit(Phi) (max |gelu_fit - gelu_erf| = 1.2e-5 over all x, checked in
 // float32 including the approximate ex2/rcp; i.e. < 1/100 of a bf16 ulp of the output wherever |y| >= 0.25).
-// 5 FMA-pipe + 2 MUFU + 2 ALU instructions, branch free.
+// 5 FMA-pipe + 2 MUFU + 1 ALU instructions, branch free.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-  const float x2 = xc * xc;
+  const float x2 = fminf(x * x, 36.0f);        // (see gelu_erf2: clamping x^2 alone is enough)
   float p = 2.4836384909576736e-05f;           // coefficients pre-multiplied by -log2(e)
   p = fmaf(p, x2, 7.3606101796031e-04f);
   p = fmaf(p, x2, -1.0598272830247879e-01f);
   p = fmaf(p, x2, -2.301647186279297f);
-  const float e = fast_ex2(p * xc);            // exp(-u)
+  const float e = fast_ex2(p * x);             // exp(-u)
   return x * fast_rcp(1.0f + e);
 }
 // the same on a pair (identical per-lane arithmetic, half the FMA-pipe instructions)
 __device__ __forceinline__ void gelu_erf2(float& a, float& b) {
-  const float ac = fminf(fmaxf(a, -6.0f), 6.0f), bc = fminf(fmaxf(b, -6.0f), 6.0f);
-  const f32x2 xc = f2_make(ac, bc);
-  const f32x2 x2 = f2_mul(xc, xc);
+  // only x^2 is clamped (one FMNMX per value): beyond |x| = 6 the exponent keeps growing linearly with the
+  // unclamped x, which only pushes Phi further towards its 0 / 1 limit
+  const f32x2 x = f2_make(a, b);
+  float t0, t1;
+  f2_get(f2_mul(x, x), t0, t1);
+  const f32x2 x2 = f2_make(fminf(t0, 36.0f), fminf(t1, 36.0f));
   f32x2 p = f2_fma(f2_make(2.4836384909576736e-05f, 2.4836384909576736e-05f), x2,
                    f2_make(7.3606101796031e-04f, 7.3606101796031e-04f));
   p = f2_fma(p, x2, f2_make(-1.0598272830247879e-01f, -1.0598272830247879e-01f));
   p = f2_fma(p, x2, f2_make(-2.301647186279297f, -2.301647186279297f));
   float u0, u1;
-  f2_get(f2_mul(p, xc), u0, u1);
+  f2_get(f2_mul(p, x), u0, u1);
   const f32x2 d = f2_add(f2_make(fast_ex2(u0), fast_ex2(u1)), f2_make(1.0f, 1.0f));
   float d0, d1;
   f2_get(d, d0, d1);
-  f2_get(f2_mul(f2_make(a, b), f2_make(fast_rcp(d0), fast_rcp(d1))), a, b);
+  f2_get(f2_mul(x, f2_make(fast_rcp(d0), fast_rcp(d1))), a, b);
 }
 
 }  // namespace b200

@@ -59,6 +59,8 @@ struct Gemm2Params {
   float ln_inv_dim, ln_eps;
   const float* col_s;
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
+  int l2_prefetch;   // A tiles are prefetched into L2 this many k blocks ahead of the shared-memory pipeline (0: off)
+  int feed_skip;     // experiment (debug key 8): load the B tile only every (feed_skip+1)-th k block (WRONG results)
 };
 
 // LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32), on fp32 PAIRS (FFMA2):
@@ -73,11 +75,11 @@ __device__ __forceinline__ void epilogue_math(float (&v)[W], int col0, int flags
     const f32x2 k2 = f2_make(k, k), r2 = f2_make(fold ? rstd : 1.0f, fold ? rstd : 1.0f);
 #pragma unroll
     for (int j = 0; j < W; j += 4) {
+      // columns at or beyond N are clipped by the TMA store: read any valid address for them instead of branching
+      const int cj = min(col0 + j, p.N - 4);
       float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + j < p.N) {
-        if (fold) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + col0 + j));
-        if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      }
+      if (fold) s4 = __ldg(reinterpret_cast<const float4*>(p.col_s + cj));
+      if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cj));
       f32x2 c01 = f2_make(b4.x, b4.y), c23 = f2_make(b4.z, b4.w);
       if (fold) {
         c01 = f2_fma(k2, f2_make(s4.x, s4.y), c01);
@@ -124,7 +126,8 @@ __device__ __forceinline__ void prefetch_cols(const Gemm2Params& p, int flags, i
   }
 }
 
-template <int MODE>
+// CTF: the epilogue flags as a compile-time constant (the inner loops then carry no flag tests), or -1 = read p.flags
+template <int MODE, int CTF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::Cfg<MODE>::NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmResid,
@@ -160,7 +163,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], p.feed_skip >= 2000 ? 2 : 1);  // (no-load experiment: the peer arrives explicitly)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -198,14 +201,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_blk = tile % p.num_n_tiles;
         const int m0 = m_pair * (2 * BLOCK_M) + rank * BLOCK_M;
         const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);
+        if (p.l2_prefetch > 0 && tile == cluster_id) {  // first tile: warm the head of its A panel
+          for (int kb = 0; kb < p.l2_prefetch && kb < p.num_k_blocks; ++kb) tma_prefetch_l2_2d(&tmA, kb * BLOCK_K, m0);
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          if (p.l2_prefetch > 0) {
+            // the A panel streams from HBM (it is the previous kernel's output and larger than L2): request it
+            // l2_prefetch k blocks ahead, across the tile boundary, so the smem ring only has to cover L2 latency
+            const int kp = kb + p.l2_prefetch;
+            if (kp < p.num_k_blocks) {
+              tma_prefetch_l2_2d(&tmA, kp * BLOCK_K, m0);
+            } else if (tile + num_clusters < num_tiles && kp - p.num_k_blocks < p.num_k_blocks) {
+              const int m_next = ((tile + num_clusters) / p.num_n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
+              tma_prefetch_l2_2d(&tmA, (kp - p.num_k_blocks) * BLOCK_K, m_next);
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          tma_load_2d_cg2(sa, &tmA, full_leader, kb * BLOCK_K, m0);
-          tma_load_2d_cg2(sb, &tmB, full_leader, kb * BLOCK_K, n0);
+          const bool load_b = p.feed_skip == 0 || (kb % (p.feed_skip + 1)) == 0;
+          const bool load_a = p.feed_skip < 2000 || kb == 0;  // >= 2000: no operand loads after the first k block
+          const uint32_t bytes = (load_a ? 2 * A_BYTES : 0) + (load_b ? 2 * (STAGE_BYTES - A_BYTES) : 0);
+          if (leader) {
+            if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            else mbar_arrive(&full_bar[stage]);
+          } else if (p.feed_skip >= 2000) {
+            mbar_arrive_cluster(full_leader);  // keeps the peer's producer in lock step when nothing is loaded
+          }
+          if (load_a) tma_load_2d_cg2(sa, &tmA, full_leader, kb * BLOCK_K, m0);
+          if (load_b) tma_load_2d_cg2(sb, &tmB, full_leader, kb * BLOCK_K, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -302,7 +327,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int e = warp - 4;
     const int quad = warp & 3;
     const int col_off = (e >> 2) * COLS_PER_WARP;
-    const int flags = p.flags;
+    const int flags = CTF >= 0 ? CTF : p.flags;
     const uint32_t tmem_empty_leader0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -497,6 +522,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+static int g_gemm_l2_prefetch = 0;
+void gemm2_set_l2_prefetch(int v) { g_gemm_l2_prefetch = v; }
+static int g_gemm_feed_skip = 0;  // experiment knob, see Gemm2Params::feed_skip
+void gemm2_set_feed_skip(int v) { g_gemm_feed_skip = v; }
 static int g_gemm_force = 0;  // debug: 0 auto, 1 force v1, 2 force v2 (wherever its epilogue applies)
 
 int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_bf16, const float* out_f32,
@@ -521,12 +550,12 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
   return (M >= 1024 && N >= 256) ? 1 : 0;    // small problems: the single-CTA kernel has finer tiles
 }
 
-template <int MODE>
+template <int MODE, int CTF>
 static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmResid, const CUtensorMap& tmOutB, const Gemm2Params& p, int clusters,
                           cudaStream_t stream) {
   using C = g2::Cfg<MODE>;
-  auto kern = gemm2_kernel<MODE>;
+  auto kern = gemm2_kernel<MODE, CTF>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
@@ -557,6 +586,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.ln_inv_dim = 1.0f / (float)K;
   p.ln_eps = ln_eps;
   p.col_s = col_s;
+  p.feed_skip = g_gemm_feed_skip;
+  p.l2_prefetch = g_gemm_l2_prefetch;
 
   CUtensorMap tmA, tmB, tmOut, tmResid, tmOutB;
   {
@@ -599,11 +630,21 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
+#define B200_G2_LAUNCH(MODE, CTF) launch_gemm2_t<MODE, CTF>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream)
+  constexpr int F_BIAS = B200VIT_EPI_BIAS, F_GELU = B200VIT_EPI_GELU, F_RES = B200VIT_EPI_RESIDUAL,
+                F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS;
+  // the flag combinations of a transformer block get their own instantiation, anything else the generic kernel
   if (dual) {
-    return launch_gemm2_t<MODE_DUAL>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+    if (flags == (F_BIAS | F_RES | F_STATS)) return B200_G2_LAUNCH(MODE_DUAL, F_BIAS | F_RES | F_STATS);
+    if (flags == (F_RES | F_STATS)) return B200_G2_LAUNCH(MODE_DUAL, F_RES | F_STATS);
+    return B200_G2_LAUNCH(MODE_DUAL, -1);
   }
-  if (out_f32) return launch_gemm2_t<MODE_F32>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
-  return launch_gemm2_t<MODE_BF16>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream);
+  if (out_f32) return B200_G2_LAUNCH(MODE_F32, -1);
+  if (flags == (F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_FOLD | F_BIAS);
+  if (flags == (F_FOLD | F_BIAS | F_GELU)) return B200_G2_LAUNCH(MODE_BF16, F_FOLD | F_BIAS | F_GELU);
+  if (flags == (F_BIAS | F_GELU)) return B200_G2_LAUNCH(MODE_BF16, F_BIAS | F_GELU);
+  return B200_G2_LAUNCH(MODE_BF16, -1);
+#undef B200_G2_LAUNCH
 }
 
 void gemm_force_version(int v) { g_gemm_force = v; }

@@ -46,6 +46,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
                  const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
                  const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream);
 void gemm_force_version(int v);
+void gemm2_set_feed_skip(int v);
+void gemm2_set_l2_prefetch(int v);
 
 int num_sms();
 
