@@ -146,7 +146,11 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
  * key 1: attention variant (0 = auto, 1 = one CTA per SM, 2 / 3 = 8 softmax warps per score tile); key 2/3: V descriptor
  * LBO / SBO bytes; key 7: FMA-pipe exp2 for 0 / 8 / 16 of every 32 softmax exponentials;
  * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies);
- * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation). */
+ * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation);
+ * key 8: CTA-pair GEMM operand-feed probe (thin out / drop the TMA operand loads -- WRONG results, timing only);
+ * key 9: CTA-pair GEMM: prefetch the A panel into L2 this many k blocks ahead (0 = off, the default);
+ * key 10: CTA-pair GEMM: use only this many stages of the operand ring (0 = all).
+ * Any attention knob selects a separately compiled debug instantiation; the production kernels carry no knob code. */
 int b200vit_debug_set(int key, int value);
 /* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention */
 void b200vit_debug_set_trace(void* dev_buf);

@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-# >= 0: feed_skip value (debug key 8);  < 0: L2 prefetch distance in k blocks (debug key 9), correct results
+# 0..9999: feed_skip value (debug key 8);  < 0: L2 prefetch distance in k blocks (debug key 9);
+# 10000 + s: use only s stages of the operand ring (debug key 10).  The last two give correct results.
 MODES = [int(a) for a in sys.argv[1:]] or [0, 1000, 3000]
 
 
@@ -24,7 +25,8 @@ def main():
     from vit_pytorch_b200 import _lib
     L = _lib.lib()
     dev = "cuda"
-    M = 512 * 197
+    M = int(os.environ.get("PROBE_M", 512 * 197))
+    do_flush = os.environ.get("PROBE_FLUSH", "1") == "1"   # 0: operands stay L2-resident between launches
     torch.manual_seed(0)
     x768 = torch.randn(M, 768, device=dev).bfloat16()
     x3072 = torch.randn(M, 3072, device=dev).bfloat16()
@@ -56,14 +58,16 @@ def main():
                                      col_s=col_s)
         row = {}
         for skip in MODES:
-            L.b200vit_debug_set(8, skip if skip >= 0 else 0)
+            L.b200vit_debug_set(8, skip if 0 <= skip < 10000 else 0)
             L.b200vit_debug_set(9, -skip if skip < 0 else 0)
+            L.b200vit_debug_set(10, skip - 10000 if skip >= 10000 else 0)
             for _ in range(3):
                 call()
             torch.cuda.synchronize()
             ts = []
             for _ in range(10):
-                flush.zero_()
+                if do_flush:
+                    flush.zero_()
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -77,6 +81,7 @@ def main():
             row[f"skip{skip}_tflops"] = round(2.0 * M * N * K / us / 1e6, 1)
         L.b200vit_debug_set(8, 0)
         L.b200vit_debug_set(9, 0)
+        L.b200vit_debug_set(10, 0)
         results[name] = row
         print(name, row, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

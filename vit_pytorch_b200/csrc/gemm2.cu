@@ -60,6 +60,7 @@ struct Gemm2Params {
   const float* col_s;
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
   int l2_prefetch;   // A tiles are prefetched into L2 this many k blocks ahead of the shared-memory pipeline (0: off)
+  int stage_limit;   // experiment (debug key 10): use only this many of the operand ring's stages (0: all)
   int feed_skip;     // experiment (debug key 8): load the B tile only every (feed_skip+1)-th k block (WRONG results)
 };
 
@@ -188,6 +189,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_base_smem;
 
   const int num_tiles = p.num_m_pairs * p.num_n_tiles;
+  const int nst = (p.stage_limit > 0 && p.stage_limit < STAGES) ? p.stage_limit : STAGES;  // (pipeline-depth probe)
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -220,8 +222,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          const bool load_b = p.feed_skip == 0 || (kb % (p.feed_skip + 1)) == 0;
-          const bool load_a = p.feed_skip < 2000 || kb == 0;  // >= 2000: no operand loads after the first k block
+          // feed_skip: 1..1999 B only every (s+1)-th k block; 2000..3999 neither A nor B after the first k block;
+          // >= 4000 A only on the first k block, B always
+          const bool load_b = p.feed_skip == 0 || p.feed_skip >= 4000 || (kb % (p.feed_skip + 1)) == 0;
+          const bool load_a = p.feed_skip < 2000 || kb == 0;
           const uint32_t bytes = (load_a ? 2 * A_BYTES : 0) + (load_b ? 2 * (STAGE_BYTES - A_BYTES) : 0);
           if (leader) {
             if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes);
@@ -231,7 +235,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (load_a) tma_load_2d_cg2(sa, &tmA, full_leader, kb * BLOCK_K, m0);
           if (load_b) tma_load_2d_cg2(sb, &tmB, full_leader, kb * BLOCK_K, n0);
-          if (++stage == STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -260,7 +264,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k = 0; k < BLOCK_K / 16; ++k)
             umma_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_mc(&empty_bar[stage], 0x3);
-          if (++stage == STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -333,6 +337,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint8_t* buf0 = epi_smem + e * C::BUFS_PER_WARP * EPI_BUF_BYTES;
     uint8_t* my_row0 = buf0 + lane * 128;  // this thread's 128-byte row inside a staging box
+    const uint32_t my_row0_s = smem_u32(my_row0);
     int acc = 0;
     uint32_t acc_phase = 0;
 
@@ -386,14 +391,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           epilogue_math<16>(v, col_base + cidx * 16, flags, mu, rstd, p);
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
-            pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-            pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-            pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-            *reinterpret_cast<uint4*>(my_row0 + ((static_cast<uint32_t>(cidx * 2 + q) ^ sw) << 4)) = pk;
-          }
+          for (int q = 0; q < 2; ++q)
+            sts_v4(my_row0_s + ((static_cast<uint32_t>(cidx * 2 + q) ^ sw) << 4),
+                   pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
         };
         tmem_ld_wait();
         tmem_ld_32x32b_x16(t_row + 16, rb);
@@ -452,15 +453,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           epilogue_math<32>(v, n_blk * BLOCK_N + col_off + c, flags, mu, rstd, p);
 
-          uint8_t* myrow = my_row0 + (box_seq & 1) * EPI_BUF_BYTES;
+          const uint32_t myrow_s = my_row0_s + (box_seq & 1) * EPI_BUF_BYTES;
           mbar_wait(&in_bar[box_seq & 1], (box_seq >> 1) & 1);  // residual box landed / buffer free
           if (has_resid) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float4* sp = reinterpret_cast<float4*>(myrow + ((static_cast<uint32_t>(q) ^ sw) << 4));
-              float4 x = *sp;
+              const uint32_t sp = myrow_s + ((static_cast<uint32_t>(q) ^ sw) << 4);
+              float4 x = lds_v4f(sp);
               x.x += v[4 * q]; x.y += v[4 * q + 1]; x.z += v[4 * q + 2]; x.w += v[4 * q + 3];
-              *sp = x;
+              sts_v4f(sp, x.x, x.y, x.z, x.w);
               if (DUAL) {
                 v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
               }
@@ -469,7 +470,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               // bf16 copy of the new residual rows (A operand of the next, LN-folded GEMM) + its row statistics
               const int half = (c >> 5) & 1;
               if (half == 0) mbar_wait(&bbuf_free[e], ((box_seq >> 1) & 1) ^ 1);  // previous pair's store has read it
-              uint8_t* brow = bbuf + lane * 128;
+              const uint32_t brow_s = smem_u32(bbuf) + lane * 128;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint4 pk;
@@ -477,7 +478,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
                 pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
                 pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-                *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4)) = pk;
+                sts_v4(brow_s + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pk.x, pk.y, pk.z, pk.w);
                 const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -491,8 +492,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(myrow + ((static_cast<uint32_t>(q) ^ sw) << 4)) =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              sts_v4f(myrow_s + ((static_cast<uint32_t>(q) ^ sw) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2],
+                      v[4 * q + 3]);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -524,6 +525,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 static int g_gemm_l2_prefetch = 0;
 void gemm2_set_l2_prefetch(int v) { g_gemm_l2_prefetch = v; }
+static int g_gemm_stage_limit = 0;
+void gemm2_set_stage_limit(int v) { g_gemm_stage_limit = v; }
 static int g_gemm_feed_skip = 0;  // experiment knob, see Gemm2Params::feed_skip
 void gemm2_set_feed_skip(int v) { g_gemm_feed_skip = v; }
 static int g_gemm_force = 0;  // debug: 0 auto, 1 force v1, 2 force v2 (wherever its epilogue applies)
@@ -588,6 +591,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.col_s = col_s;
   p.feed_skip = g_gemm_feed_skip;
   p.l2_prefetch = g_gemm_l2_prefetch;
+  p.stage_limit = g_gemm_stage_limit;
 
   CUtensorMap tmA, tmB, tmOut, tmResid, tmOutB;
   {

@@ -48,6 +48,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
 void gemm_force_version(int v);
 void gemm2_set_feed_skip(int v);
 void gemm2_set_l2_prefetch(int v);
+void gemm2_set_stage_limit(int v);
 
 int num_sms();
 
