@@ -33,6 +33,7 @@ extern "C" {
 #define B200VIT_EPI_RESIDUAL 4  /* + resid[m, n] (fp32); resid may alias out_f32 (in-place residual stream) */
 #define B200VIT_EPI_LNFOLD 8    /* A is the un-normalised bf16 row, W carries gamma: y = rstd_m*(acc - mu_m*s_n) + bias_n */
 #define B200VIT_EPI_STATS 16    /* write per-row partial (sum, sum^2) of the bf16-rounded result into stats_out */
+#define B200VIT_EPI_HEADNORM 32 /* internal to b200vit_gemm_headnorm_bf16: RMS-normalise leading 64-wide heads */
 
 const char* b200vit_last_error(void);
 int b200vit_version(void);
@@ -130,6 +131,36 @@ int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int32_t* dims_
 int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H, int dh, void* stream);
 
 /*
+ * Linear + per-head RMSNorm in one pass (NaViT to_q / to_kv followed by q_norm / k_norm, na_vit.py:145-150):
+ *   out[M, N] bf16 = epilogue(A W^T)   with flags in {EPI_BIAS, EPI_LNFOLD} exactly as b200vit_gemm_bf16, then the first
+ *   norm_heads heads (dh = 64 columns each, from column 0) of every row are replaced by
+ *   v / max(||v||, 1e-12) * sqrt(dh) * head_gamma[h, d]   (norm computed on the bf16-rounded projection, like the
+ *   reference's bf16 module).  Large problems run the RMSNorm inside the CTA-pair GEMM epilogue (one warp owns one
+ *   head of 32 rows); small ones run b200vit_gemm_bf16 + b200vit_rmsnorm_heads.
+ */
+int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, int64_t ldo,
+                               const float* bias, const float* ln_sums, int ln_parts, float ln_eps,
+                               const float* col_s, const float* head_gamma, int norm_heads, int dh, int M, int N,
+                               int K, int flags, void* stream);
+
+/*
+ * The same normalisation on any row-major bf16 buffer: the `nheads` consecutive dh-wide heads that start at column 0
+ * of every row buf[t*ld ...] (the k half of a [k | v] buffer for the attention pooling, na_vit.py:143-150);
+ * gamma fp32 [nheads][dh].  ld in elements, multiple of 8; buf 16-byte aligned.
+ */
+int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, void* stream);
+
+/*
+ * NaViT token assembly on the packed [T, D] matrix (na_vit.py:228,350-359): x = LayerNorm(y; gamma, no bias)
+ * + pos_h[row of the token in its image's patch grid] + pos_w[column]; optional bf16 copy xb and stats[T][2] =
+ * (sum, sum of squares) of that copy (entry statistics of the LN-folded layer chain, as b200vit_embed_tokens).
+ * cu_seqlens_dev[S+1]; dims_dev[S][2] = (H_s, W_s) in pixels (grid width = W_s / p).  D multiple of 4.
+ */
+int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h, const float* pos_w,
+                         const int32_t* cu_seqlens_dev, const int32_t* dims_dev, float* x, void* xb_bf16,
+                         float* stats, int T, int D, int S, int p, float eps, void* stream);
+
+/*
  * NaViT attention pooling (na_vit.py:371-387): out[s, h*dh:(h+1)*dh] = softmax_j(qn_h . k_jh) v_jh over the tokens j of
  * sequence s; kv[T, 2*H*dh] bf16 (k normalised, then v), qn[H*dh] fp32, cu_seqlens_dev[S+1] device int32, scale 1.
  */
@@ -149,7 +180,8 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
  * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation);
  * key 8: CTA-pair GEMM operand-feed probe (thin out / drop the TMA operand loads -- WRONG results, timing only);
  * key 9: CTA-pair GEMM: prefetch the A panel into L2 this many k blocks ahead (0 = off, the default);
- * key 10: CTA-pair GEMM: use only this many stages of the operand ring (0 = all).
+ * key 10: CTA-pair GEMM: use only this many stages of the operand ring (0 = all);
+ * key 11: varlen attention kernel (0 = pipelined 64-key blocks, the default; 1 = serial 128-key blocks).
  * Any attention knob selects a separately compiled debug instantiation; the production kernels carry no knob code. */
 int b200vit_debug_set(int key, int value);
 /* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention */

@@ -58,15 +58,21 @@ def test_navit_varied_resolutions_against_oracle():
     assert mx < 3e-2 and frac > 0.80
 
 
-def test_varlen_attention_kernel_against_oracle():
-    lengths = [197, 1, 130, 577, 64, 1024, 129]
+@pytest.mark.parametrize("mode", [0, 1])      # 0: pipelined 64-key blocks (default); 1: serial 128-key blocks
+def test_varlen_attention_kernel_against_oracle(mode):
+    lengths = [197, 1, 130, 577, 64, 1024, 129, 65, 63, 128, 300]
     H, dh = 3, 64
     T = sum(lengths)
     torch.manual_seed(0)
     qkv = torch.randn(T, 3 * H * dh, device=DEV).bfloat16()
     out = torch.zeros(T, H * dh, device=DEV, dtype=torch.bfloat16)
     cu, tp, tiles = _lib.varlen_index(lengths, DEV)
-    _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, dh ** -0.5)
+    _lib.lib().b200vit_debug_set(11, mode)
+    try:
+        _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, dh ** -0.5)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().b200vit_debug_set(11, 0)
     ref = torch.empty(T, H * dh)
     o = 0
     for n in lengths:
@@ -77,9 +83,10 @@ def test_varlen_attention_kernel_against_oracle():
     assert frac > 0.995 and mx < 2e-2, (mx, mean, frac)
 
 
-def test_qk_rmsnorm_and_attn_pool_kernels():
+@pytest.mark.parametrize("H", [3, 4, 16])
+def test_qk_rmsnorm_and_attn_pool_kernels(H):
     torch.manual_seed(1)
-    T, H, dh = 300, 4, 64
+    T, dh = 300, 64
     I = H * dh
     qkv = torch.randn(T, 3 * I, device=DEV).bfloat16()
     g = torch.randn(2, H, dh, device=DEV)
@@ -102,3 +109,102 @@ def test_qk_rmsnorm_and_attn_pool_kernels():
         want = torch.einsum("hn,nhd->hd", sc.softmax(-1), v).reshape(-1)
         assert torch.allclose(out[i].float(), want, rtol=2e-2, atol=2e-2)
         o += n
+
+
+def test_rmsnorm_heads_on_the_k_half_of_a_kv_buffer():
+    torch.manual_seed(2)
+    T, H, dh = 77, 5, 64
+    I = H * dh
+    kv = torch.randn(T, 2 * I, device=DEV).bfloat16()
+    g = torch.randn(H, dh, device=DEV)
+    before = kv.clone()
+    _lib.rmsnorm_heads(kv, g.reshape(-1).contiguous(), H, dh)
+    want = NO.rms_norm_heads(before[:, :I].float().view(T, H, dh).permute(1, 0, 2).cpu(), g.cpu()[:, None, :])
+    assert torch.allclose(kv[:, :I].float().view(T, H, dh).permute(1, 0, 2).cpu(), want, rtol=1e-2, atol=1e-2)
+    assert torch.equal(kv[:, I:], before[:, I:])                      # v untouched
+
+
+def test_embed_varlen_matches_torch():
+    torch.manual_seed(5)
+    p, D = 16, 192
+    sizes = [(48, 32), (16, 16), (64, 80), (32, 128)]
+    imgs = [torch.empty(3, h, w, device=DEV, dtype=torch.bfloat16) for h, w in sizes]
+    ix = _lib.VarlenIndex(imgs, p, DEV)
+    T = ix.T
+    y = torch.randn(T, D, device=DEV)
+    gamma = torch.randn(D, device=DEV)
+    pos_h, pos_w = torch.randn(9, D, device=DEV), torch.randn(9, D, device=DEV)
+    x = torch.empty(T, D, device=DEV)
+    xb = torch.empty(T, D, device=DEV, dtype=torch.bfloat16)
+    st = torch.empty(T, 1, 2, device=DEV)
+    _lib.embed_varlen(y, gamma, pos_h, pos_w, ix, x, p, xb=xb, stats=st)
+    hi = torch.cat([torch.arange(h // p).repeat_interleave(w // p) for h, w in sizes]).to(DEV)
+    wi = torch.cat([torch.arange(w // p).repeat(h // p) for h, w in sizes]).to(DEV)
+    want = torch.nn.functional.layer_norm(y, (D,), gamma, None) + pos_h[hi] + pos_w[wi]
+    assert torch.allclose(x, want, rtol=1e-5, atol=1e-5)
+    assert torch.equal(xb, x.bfloat16())
+    xf = xb.float()
+    assert torch.allclose(st[:, 0, 0], xf.sum(1), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(st[:, 0, 1], (xf * xf).sum(1), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("misalign", [False, True])
+def test_patchify_varlen_ln_fast_path(misalign):
+    """p = 16 kernel: 16-byte staged images and element-wise staged (2-byte aligned) images give the reference
+    'c (h p1) (w p2) -> (h w) (c p1 p2)' + LayerNorm(no bias)."""
+    torch.manual_seed(6)
+    p, C = 16, 3
+    sizes = [(32, 48), (16, 16), (80, 512), (48, 16)]
+    imgs = []
+    for h, w in sizes:
+        flat = torch.randn(C * h * w + 8, device=DEV).bfloat16()
+        off = 1 if misalign else 0
+        imgs.append(flat[off:off + C * h * w].view(C, h, w))
+        assert imgs[-1].is_contiguous() and (imgs[-1].data_ptr() % 16 == 0) == (not misalign)
+    ix = _lib.VarlenIndex(imgs, p, DEV)
+    gamma = torch.randn(C * p * p, device=DEV)
+    out = torch.empty(ix.T, C * p * p, device=DEV, dtype=torch.bfloat16)
+    _lib.patchify_varlen_ln(imgs, gamma, out, ix.cu, p, index=ix)
+    want = torch.cat([torch.nn.functional.layer_norm(NO.patchify_cpp(im.float().cpu(), p), (C * p * p,), gamma.cpu(), None)
+                      for im in imgs])
+    assert torch.allclose(out.float().cpu(), want, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fold"])
+def test_navit_ln_modes_agree_with_golden(mode, monkeypatch):
+    monkeypatch.setenv("B200VIT_LN_MODE", mode)
+    g = load_golden("navit_tiny")
+    m = NaViT(**g["kwargs"]).eval()
+    m.load_state_dict(g["state_dict"])
+    m = m.to(DEV, torch.bfloat16)
+    rows = [[g["images"][i].to(DEV) for i in r] for r in g["rows"]]
+    with torch.inference_mode():
+        out = m(rows)
+    mx, mean, frac = _stats(out, g["logits_fp32"])
+    print(f"navit_tiny {mode}: max {mx:.5f} mean {mean:.5f} within {frac:.4f}")
+    assert mx < 1.5e-2 and frac > 0.85
+
+
+@pytest.mark.parametrize("M", [300, 5000])           # small: GEMM + rmsnorm_heads; large: fused CTA-pair epilogue
+@pytest.mark.parametrize("fold", [False, True])
+def test_gemm_headnorm_matches_gemm_then_rmsnorm(M, fold):
+    torch.manual_seed(8)
+    H, dh, K = 4, 64, 256
+    I = H * dh
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(3 * I, K, device=DEV) / K ** 0.5).bfloat16()
+    g = torch.randn(2 * I, device=DEV)
+    kw = {}
+    if fold:
+        af = a.float()
+        kw = dict(bias=torch.randn(3 * I, device=DEV), col_s=w.float().sum(1).contiguous(),
+                  ln_sums=torch.stack([af.sum(1), (af * af).sum(1)], 1).contiguous())
+    want = torch.empty(M, 3 * I, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(a, w, out_bf16=want, **kw)
+    v_part = want[:, 2 * I:].clone()
+    _lib.qk_rmsnorm(want, g, H, dh)
+    got = torch.empty_like(want)
+    _lib.gemm_headnorm(a, w, out_bf16=got, head_gamma=g, norm_heads=2 * H, **kw)
+    assert torch.equal(got[:, 2 * I:], v_part)                          # v columns untouched
+    d = (got.float() - want.float()).abs()
+    assert (d <= 1e-3 + 1e-2 * want.float().abs()).float().mean() > 0.999, d.max()

@@ -27,7 +27,8 @@ SYMBOLS = [
     "b200vit_device_ok", "b200vit_gemm_bf16", "b200vit_layernorm", "b200vit_patchify_ln", "b200vit_embed_tokens",
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
-    "b200vit_patchify_varlen_ln",
+    "b200vit_patchify_varlen_ln", "b200vit_rmsnorm_heads", "b200vit_embed_varlen",
+    "b200vit_gemm_headnorm_bf16",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -58,6 +59,9 @@ def lib() -> C.CDLL:
     L.b200vit_gemm_bf16.restype = i32
     L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
                                     vp]
+    L.b200vit_gemm_headnorm_bf16.restype = i32
+    L.b200vit_gemm_headnorm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
+                                             i32, i32, vp]
     L.b200vit_stats_parts.restype = i32
     L.b200vit_stats_parts.argtypes = [i32]
     L.b200vit_layernorm.restype = i32
@@ -78,6 +82,10 @@ def lib() -> C.CDLL:
     L.b200vit_patchify_varlen_ln.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_qk_rmsnorm.restype = i32
     L.b200vit_qk_rmsnorm.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.b200vit_rmsnorm_heads.restype = i32
+    L.b200vit_rmsnorm_heads.argtypes = [vp, i64, vp, i32, i32, i32, vp]
+    L.b200vit_embed_varlen.restype = i32
+    L.b200vit_embed_varlen.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
     L.b200vit_attn_pool.restype = i32
     L.b200vit_attn_pool.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.b200vit_mean_pool.restype = i32
@@ -202,6 +210,33 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
     _check(rc, "b200vit_gemm_bf16")
 
 
+def gemm_headnorm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: torch.Tensor, head_gamma: torch.Tensor,
+                  norm_heads: int, dh: int = 64, bias: Optional[torch.Tensor] = None,
+                  ln_sums: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+                  col_s: Optional[torch.Tensor] = None) -> None:
+    """out = epilogue(a @ w^T) with the first norm_heads heads of every row RMS-normalised (NaViT q / k norm)."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+    for nm, t in (("bias", bias), ("ln_sums", ln_sums), ("col_s", col_s), ("head_gamma", head_gamma)):
+        _chk(t, torch.float32, nm)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and out_bf16.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert head_gamma.is_contiguous() and head_gamma.numel() == norm_heads * dh
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    ln_parts = 0
+    if ln_sums is not None:
+        flags |= EPI_LNFOLD
+        assert ln_sums.is_contiguous() and ln_sums.shape[0] == M and ln_sums.shape[-1] == 2
+        ln_parts = 1 if ln_sums.dim() == 2 else ln_sums.shape[1]
+    with _Timed("gemm", M=M, N=N, K=K, flags=flags | 32, flops=2.0 * M * N * K):
+        rc = lib().b200vit_gemm_headnorm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16),
+                                              out_bf16.stride(0), _ptr(bias), _ptr(ln_sums), ln_parts, float(ln_eps),
+                                              _ptr(col_s), _ptr(head_gamma), norm_heads, dh, M, N, K, flags, _stream())
+    _check(rc, "b200vit_gemm_headnorm_bf16")
+
+
 def stats_parts(n: int) -> int:
     return int(lib().b200vit_stats_parts(int(n)))
 
@@ -295,27 +330,81 @@ def attention_varlen(qkv: torch.Tensor, out: torch.Tensor, cu_seqlens: torch.Ten
     _check(rc, "b200vit_attention_varlen")
 
 
+class VarlenIndex:
+    """Device-side index arrays of a packed batch of variable-size images, built on the host and moved with ONE
+    host->device copy: cu_seqlens[S+1] (token offsets), tile_prefix[S+1] (128-row query tiles, attention_varlen),
+    dims[S][2] = (H, W) pixels, row_prefix[S+1] (patch rows), img_ptrs[S] (int64 addresses)."""
+
+    def __init__(self, images, p: int, device) -> None:
+        S = len(images)
+        cu, tp, rows, dims, ptrs = [0], [0], [0], [], []
+        for im in images:
+            hh, ww = int(im.shape[-2]), int(im.shape[-1])
+            n = (hh // p) * (ww // p)
+            cu.append(cu[-1] + n)
+            tp.append(tp[-1] + (n + 127) // 128)
+            rows.append(rows[-1] + hh // p)
+            dims += [hh, ww]
+            ptrs.append(im.data_ptr())
+        n32 = 3 * (S + 1) + 2 * S
+        host = torch.empty(S + (n32 + 1) // 2, dtype=torch.int64)
+        host[:S] = torch.tensor(ptrs, dtype=torch.int64)
+        host[S:].view(torch.int32)[:n32] = torch.tensor(cu + tp + rows + dims, dtype=torch.int32)
+        dev = host.to(device)
+        i32 = dev[S:].view(torch.int32)
+        self.img_ptrs = dev[:S]
+        self.cu = i32[:S + 1]
+        self.tile_prefix = i32[S + 1:2 * (S + 1)]
+        self.row_prefix = i32[2 * (S + 1):3 * (S + 1)]
+        self.dims = i32[3 * (S + 1):3 * (S + 1) + 2 * S]
+        self.S, self.T, self.total_tiles, self.total_rows = S, cu[-1], tp[-1], rows[-1]
+        self.max_w = max(dims[1::2])
+        self.lengths = [cu[i + 1] - cu[i] for i in range(S)]
+
+
 def patchify_varlen_ln(images, gamma: torch.Tensor, out_bf16: torch.Tensor, cu_seqlens: torch.Tensor, p: int,
-                       eps: float = 1e-5) -> None:
+                       eps: float = 1e-5, index: Optional[VarlenIndex] = None) -> None:
     """images: list of contiguous CUDA bf16 [C, H, W] tensors (kept alive by the caller until the stream has run)."""
     _chk(gamma, torch.float32, "gamma"); _chk(out_bf16, torch.bfloat16, "out")
     dev = out_bf16.device
     C = images[0].shape[0]
-    ptrs, dims, rows = [], [], [0]
     for im in images:
         assert im.is_cuda and im.dtype == torch.bfloat16 and im.is_contiguous() and im.shape[0] == C
-        ptrs.append(im.data_ptr())
-        dims += [im.shape[1], im.shape[2]]
-        rows.append(rows[-1] + im.shape[1] // p)
-    t_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
-    t_dims = torch.tensor(dims, dtype=torch.int32, device=dev)
-    t_rows = torch.tensor(rows, dtype=torch.int32, device=dev)
-    max_w = max(im.shape[2] for im in images)
+    ix = index if index is not None else VarlenIndex(images, p, dev)
     with _Timed("patchify_varlen_ln", bytes=out_bf16.numel() * 4):
-        rc = lib().b200vit_patchify_varlen_ln(_ptr(t_ptrs), _ptr(t_dims), _ptr(cu_seqlens), _ptr(t_rows), _ptr(gamma),
-                                              _ptr(out_bf16), out_bf16.stride(0), len(images), rows[-1], max_w, C, p,
-                                              float(eps), _stream())
+        rc = lib().b200vit_patchify_varlen_ln(_ptr(ix.img_ptrs), _ptr(ix.dims), _ptr(cu_seqlens), _ptr(ix.row_prefix),
+                                              _ptr(gamma), _ptr(out_bf16), out_bf16.stride(0), len(images),
+                                              ix.total_rows, ix.max_w, C, p, float(eps), _stream())
     _check(rc, "b200vit_patchify_varlen_ln")
+
+
+def embed_varlen(y: torch.Tensor, gamma: torch.Tensor, pos_h: torch.Tensor, pos_w: torch.Tensor, index: VarlenIndex,
+                 x: torch.Tensor, p: int, xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+                 eps: float = 1e-5) -> None:
+    for nm, t in (("y", y), ("gamma", gamma), ("pos_h", pos_h), ("pos_w", pos_w), ("x", x), ("stats", stats)):
+        _chk(t, torch.float32, nm)
+    _chk(xb, torch.bfloat16, "xb")
+    T, D = y.shape
+    assert y.is_contiguous() and x.is_contiguous() and pos_h.is_contiguous() and pos_w.is_contiguous()
+    assert T == index.T and x.shape == y.shape and pos_h.shape[1] == D and pos_w.shape[1] == D
+    assert xb is None or (xb.is_contiguous() and xb.shape == y.shape)
+    assert stats is None or (stats.is_contiguous() and stats.numel() == 2 * T)
+    with _Timed("embed_varlen", bytes=y.numel() * 10):
+        rc = lib().b200vit_embed_varlen(_ptr(y), _ptr(gamma), _ptr(pos_h), _ptr(pos_w), _ptr(index.cu),
+                                        _ptr(index.dims), _ptr(x), _ptr(xb), _ptr(stats), T, D, index.S, p,
+                                        float(eps), _stream())
+    _check(rc, "b200vit_embed_varlen")
+
+
+def rmsnorm_heads(buf: torch.Tensor, gamma: torch.Tensor, nheads: int, dh: int) -> None:
+    """In place on the first nheads*dh columns of every row of buf[T, ld]."""
+    _chk(buf, torch.bfloat16, "buf"); _chk(gamma, torch.float32, "gamma")
+    assert buf.dim() == 2 and buf.stride(1) == 1 and gamma.is_contiguous() and gamma.numel() == nheads * dh
+    assert buf.shape[1] >= nheads * dh
+    T = buf.shape[0]
+    with _Timed("rmsnorm_heads", bytes=T * nheads * dh * 4):
+        rc = lib().b200vit_rmsnorm_heads(_ptr(buf), buf.stride(0), _ptr(gamma), T, nheads, dh, _stream())
+    _check(rc, "b200vit_rmsnorm_heads")
 
 
 def qk_rmsnorm(qkv: torch.Tensor, gamma_qk: torch.Tensor, H: int, dh: int) -> None:

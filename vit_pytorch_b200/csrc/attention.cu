@@ -443,6 +443,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 8: gemm2_set_feed_skip(value); return 0;
     case 9: gemm2_set_l2_prefetch(value); return 0;
     case 10: gemm2_set_stage_limit(value); return 0;
+    case 11: attention_varlen_set_mode(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
 }

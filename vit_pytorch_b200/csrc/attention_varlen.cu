@@ -287,6 +287,296 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tm, const AttnVarlen
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined variant (the default): the same two-phase algorithm on key blocks of 64 with THREE score buffers, so that
+// Q K^T of the next two blocks is issued before the softmax warps have finished block b and before P_b V_b has
+// completed -- the MMA round trips (issue -> commit -> mbarrier -> wake-up, ~0.7 us each) that serialised every
+// 128-key step of the kernel above overlap with the exponentials.  TMEM: S|P buffers at [0,64), [64,128) and
+// [192,256) (P_b, bf16, in the first 32 columns of its own buffer), O at [128,192); 256 columns allocated, 2 CTAs per
+// SM; 4 K/V stages of 64 keys.  Per-buffer barrier phases are tracked as bit masks (bit b = parity of buffer b).
+// ---------------------------------------------------------------------------------------------------------------
+namespace av2 {
+constexpr int DH = 64;
+constexpr int KB = 64;                       // keys per block
+constexpr int Q_BYTES = 128 * 128;           // 128 rows x 64 bf16
+constexpr int KV_BYTES = KB * 128;           // 64 rows x 64 bf16
+constexpr int KV_STAGES = 4;
+constexpr int NBUF = 3;                      // score buffers
+constexpr int LOOKAHEAD = 2;                 // Q K^T is issued this many steps ahead of the softmax warps
+constexpr int SMEM_DATA = Q_BYTES + 2 * KV_BYTES * KV_STAGES;
+// q_full q_empty kv_full[4] kv_empty[4] s_full[3] s_free[3] p_ready[3] pv_done[3] o_full o_free
+constexpr int NUM_BARS = 2 + 2 * KV_STAGES + 4 * NBUF + 2;
+constexpr int DYN_BYTES = SMEM_DATA + NUM_BARS * 8 + 16 + 1024;
+constexpr int TMEM_COLS = 256;
+constexpr int O_COL = 128;
+constexpr int THREADS = 6 * 32;
+__device__ __forceinline__ uint32_t buf_col(int bf) { return bf == 2 ? 192u : static_cast<uint32_t>(bf) * KB; }
+}  // namespace av2
+
+__global__ void __launch_bounds__(av2::THREADS, 2)
+attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                         const AttnVarlenParams p) {
+  using namespace av2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + Q_BYTES;  // stage st: K at sKV + st*2*KV_BYTES, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES;  // [NBUF]
+  uint64_t* s_free = s_full + NBUF;         // [NBUF]  phase 1: the softmax warps have scanned the block
+  uint64_t* p_ready = s_free + NBUF;        // [NBUF]
+  uint64_t* pv_done = p_ready + NBUF;       // [NBUF]
+  uint64_t* o_full = pv_done + NBUF;
+  uint64_t* o_free = o_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int TMA_WARP = 4, MMA_WARP = 5;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_free[b], 4);
+      mbar_init(&p_ready[b], 4);
+      mbar_init(&pv_done[b], 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t units_done = 0, kv_count = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+        int seq, h, qt, row0, n;
+        av_locate(p, u, seq, h, qt, row0, n);
+        const int nb = (n + KB - 1) / KB;
+        mbar_wait(q_empty, (units_done & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, h * DH, row0 + qt * 128);
+        const int steps = (nb > 1 ? nb : 0) + nb;
+        for (int s = 0; s < steps; ++s, ++kv_count) {
+          const bool phase2 = s >= steps - nb;
+          const int kb = phase2 ? s - (steps - nb) : s;
+          const int st = kv_count % KV_STAGES;
+          mbar_wait(&kv_empty[st], ((kv_count / KV_STAGES) & 1) ^ 1);
+          uint8_t* k_dst = sKV + st * 2 * KV_BYTES;
+          mbar_arrive_expect_tx(&kv_full[st], phase2 ? 2 * KV_BYTES : KV_BYTES);
+          tma_load_2d(k_dst, &tmKV, &kv_full[st], p.I + h * DH, row0 + kb * KB);
+          if (phase2) tma_load_2d(k_dst + KV_BYTES, &tmKV, &kv_full[st], 2 * p.I + h * DH, row0 + kb * KB);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KB, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, DH, 0, 1);
+      const uint32_t sq = smem_u32(sQ);
+      uint32_t units_done = 0;
+      uint32_t sc = 0;   // global step counter: K/V stage = sc % KV_STAGES
+      int bf_issue = 0;  // score buffer of the next Q K^T to issue (cycles 0, 1, 2)
+      int bf_fin = 0;    // score buffer of the next step to finish (P V issue)
+      // bit b of each mask = parity of the number of completions requested so far on buffer b's barrier
+      uint32_t par_sfree = 0, par_pready = 0, par_pv = 0;
+      uint32_t owes_sfree = 0, owes_pv = 0;  // bit b: the buffer's last user still has to signal s_free / pv_done
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+        int seq, h, qt, row0, n;
+        av_locate(p, u, seq, h, qt, row0, n);
+        const int nb = (n + KB - 1) / KB;
+        const int steps = (nb > 1 ? nb : 0) + nb;
+        mbar_wait(q_full, units_done & 1);
+        const uint32_t sc0 = sc;
+        // issue Q K_b^T of step s (global step sc0 + s) into the next score buffer
+        auto issue_s = [&](int s) {
+          const uint32_t g = sc0 + s;
+          const int bf = bf_issue, st = g % KV_STAGES;
+          const uint32_t bit = 1u << bf;
+          bf_issue = bf == NBUF - 1 ? 0 : bf + 1;
+          const bool phase2 = s >= steps - nb;
+          // (parity of the LAST requested completion = current parity bit ^ 1)
+          if (owes_sfree & bit) mbar_wait(&s_free[bf], ((par_sfree >> bf) & 1) ^ 1);
+          else if (owes_pv & bit) mbar_wait(&pv_done[bf], ((par_pv >> bf) & 1) ^ 1);
+          owes_sfree &= ~bit;
+          owes_pv &= ~bit;
+          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(sq, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sKV + st * 2 * KV_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_ss(tmem_base + buf_col(bf), adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[bf]);
+          if (s == steps - 1) umma_commit(q_empty);  // last use of the Q tile
+          if (!phase2) {
+            umma_commit(&kv_empty[st]);              // phase 1 stages hold K only
+            par_sfree ^= bit;
+            owes_sfree |= bit;
+          } else {
+            owes_pv |= bit;                          // until P_b V_b (issued below, later) has completed
+          }
+        };
+        for (int s = 0; s < LOOKAHEAD && s < steps; ++s) issue_s(s);
+        for (int s = 0; s < steps; ++s) {
+          if (s + LOOKAHEAD < steps) issue_s(s + LOOKAHEAD);  // ahead of the softmax warps
+          const int bf = bf_fin;
+          bf_fin = bf == NBUF - 1 ? 0 : bf + 1;
+          const bool phase2 = s >= steps - nb;
+          if (!phase2) continue;
+          const uint32_t g = sc0 + s;
+          const int st = g % KV_STAGES;
+          const int kb = s - (steps - nb);
+          if (kb == 0) mbar_wait(o_free, (units_done & 1) ^ 1);  // previous unit's O has been read
+          mbar_wait(&p_ready[bf], (par_pready >> bf) & 1);
+          par_pready ^= 1u << bf;
+          tc_fence_after();
+          const uint32_t sv = smem_u32(sKV + st * 2 * KV_BYTES + KV_BYTES);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
+            umma_ts(tmem_base + O_COL, tmem_base + buf_col(bf) + k * 8, vdesc, idesc_pv, (kb | k) != 0);
+          }
+          umma_commit(&kv_empty[st]);
+          umma_commit(&pv_done[bf]);
+          par_pv ^= 1u << bf;
+          if (kb == nb - 1) umma_commit(o_full);
+        }
+        sc = sc0 + steps;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup (thread == query row)
+    const int quad = warp & 3;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float c = p.scale_log2e;
+    uint32_t units_done = 0;
+    int bf = 0;                // score buffer of the next step (cycles 0, 1, 2, in step order like the MMA warp)
+    uint32_t par_sfull = 0;    // bit b: parity of the next completion of s_full[b]
+    auto next_buf = [&]() {
+      par_sfull ^= 1u << bf;
+      bf = bf == NBUF - 1 ? 0 : bf + 1;
+    };
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+      int seq, h, qt, row0, n;
+      av_locate(p, u, seq, h, qt, row0, n);
+      const int nb = (n + KB - 1) / KB;
+      const int qrow = qt * 128 + quad * 32 + lane;
+      float mx = -INFINITY;
+      auto block_max = [&](int kb, uint32_t tb) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < KB; c0 += 32) {
+          if (kb * KB + c0 >= n) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tb + c0, r);
+          tmem_ld_wait();
+          const int lim = n - (kb * KB + c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < lim) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      };
+      if (nb > 1) {
+        for (int kb = 0; kb < nb; ++kb) {
+          mbar_wait(&s_full[bf], (par_sfull >> bf) & 1);
+          tc_fence_after();
+          block_max(kb, t_lane + buf_col(bf));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[bf]);
+          next_buf();
+        }
+      }
+      float sum = 0.f;
+      for (int kb = 0; kb < nb; ++kb) {
+        const uint32_t tb = t_lane + buf_col(bf);
+        mbar_wait(&s_full[bf], (par_sfull >> bf) & 1);
+        tc_fence_after();
+        if (nb == 1) block_max(0, tb);
+        const float mc = mx * c;
+#pragma unroll 1
+        for (int c0 = 0; c0 < KB; c0 += 32) {
+          uint32_t r[32];
+          uint32_t pk[16];
+          const int lim = n - (kb * KB + c0);  // number of valid keys in this chunk (may be <= 0)
+          if (lim > 0) {
+            tmem_ld_32x32b_x32(tb + c0, r);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float e0 = (j < lim) ? fast_ex2(fmaf(__uint_as_float(r[j]), c, -mc)) : 0.f;
+            const float e1 = (j + 1 < lim) ? fast_ex2(fmaf(__uint_as_float(r[j + 1]), c, -mc)) : 0.f;
+            sum += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32b_x16(tb + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[bf]);
+        next_buf();
+      }
+      // epilogue: O / sum -> bf16 -> global
+      mbar_wait(o_full, units_done & 1);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      uint32_t ob[32];
+#pragma unroll
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      if (qrow < n) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + (size_t)(row0 + qrow) * p.I + h * DH);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int g_varlen_mode = 0;  // 0: pipelined 64-key blocks (default), 1: the serial 128-key-block kernel
+void attention_varlen_set_mode(int v) { g_varlen_mode = v; }
+
 }  // namespace b200
 
 using namespace b200;
@@ -309,21 +599,38 @@ extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_
   p.units = total_tiles * H;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  CUtensorMap tm;
   const uint64_t dims[2] = {(uint64_t)3 * p.I, (uint64_t)total_tokens};
   const uint64_t strides[1] = {(uint64_t)3 * p.I * 2};
-  const uint32_t box[2] = {64, 128};
-  int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DYN_BYTES));
-    attr_set = true;
-  }
   const int slots = 2 * num_sms();
   const int grid = p.units < slots ? p.units : slots;
-  attention_varlen_kernel<<<grid, THREADS, DYN_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_varlen_mode == 0) {
+    CUtensorMap tmQ, tmKV;
+    const uint32_t qbox[2] = {64, 128}, kvbox[2] = {64, (uint32_t)av2::KB};
+    int rc = encode_tmap_bf16(&tmQ, qkv, 2, dims, strides, qbox);
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tmKV, qkv, 2, dims, strides, kvbox);
+    if (rc) return rc;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           av2::DYN_BYTES));
+      attr2_set = true;
+    }
+    attention_varlen2_kernel<<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
+  } else {
+    CUtensorMap tm;
+    const uint32_t box[2] = {64, 128};
+    int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           DYN_BYTES));
+      attr_set = true;
+    }
+    attention_varlen_kernel<<<grid, THREADS, DYN_BYTES, st>>>(tm, p);
+  }
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

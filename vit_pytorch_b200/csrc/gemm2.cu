@@ -59,6 +59,8 @@ struct Gemm2Params {
   float ln_inv_dim, ln_eps;
   const float* col_s;
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
+  const float* head_gamma;  // EPI_HEADNORM: fp32 [norm_cols] scale of the RMS-normalised leading heads
+  int norm_cols;            //               columns [0, norm_cols) are normalised per 64-wide head
   int l2_prefetch;   // A tiles are prefetched into L2 this many k blocks ahead of the shared-memory pipeline (0: off)
   int stage_limit;   // experiment (debug key 10): use only this many of the operand ring's stages (0: all)
   int feed_skip;     // experiment (debug key 8): load the B tile only every (feed_skip+1)-th k block (WRONG results)
@@ -385,16 +387,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) tma_store_wait_read<0>();  // last tile's store has finished reading the staging box
         __syncwarp();
 
+        float ss = 0.f;  // EPI_HEADNORM: sum of squares of this row's 64 (bf16-rounded) values = one head
         auto emit16 = [&](const uint32_t (&r)[16], int cidx) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           epilogue_math<16>(v, col_base + cidx * 16, flags, mu, rstd, p);
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
-            sts_v4(my_row0_s + ((static_cast<uint32_t>(cidx * 2 + q) ^ sw) << 4),
-                   pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t w0 = pack_bf16x2(v[8 * q], v[8 * q + 1]), w1 = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            const uint32_t w2 = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), w3 = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+            sts_v4(my_row0_s + ((static_cast<uint32_t>(cidx * 2 + q) ^ sw) << 4), w0, w1, w2, w3);
+            if (flags & B200VIT_EPI_HEADNORM) {
+              const uint32_t w4[4] = {w0, w1, w2, w3};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xFFFF0000u);
+                ss = fmaf(lo, lo, fmaf(hi, hi, ss));
+              }
+            }
+          }
         };
         tmem_ld_wait();
         tmem_ld_32x32b_x16(t_row + 16, rb);
@@ -408,6 +420,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_wait();
         release_tmem();
         emit16(rb, 3);
+        if ((flags & B200VIT_EPI_HEADNORM) && col_base < p.norm_cols) {
+          // this warp's 64 columns are exactly one head: every thread rescales its own row inside the staging box
+          const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);  // sqrt(dh) / max(||v||, eps)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t sp = my_row0_s + ((static_cast<uint32_t>(q) ^ sw) << 4);
+            const float4 raw = lds_v4f(sp);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.head_gamma + col_base + 8 * q));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.head_gamma + col_base + 8 * q + 4));
+            const uint32_t w[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z),
+                                   __float_as_uint(raw.w)};
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+              o[i] = pack_bf16x2(lo * inv * gg[2 * i], hi * inv * gg[2 * i + 1]);
+            }
+            sts_v4(sp, o[0], o[1], o[2], o[3]);
+          }
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -572,7 +605,8 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
                  const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
-                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream) {
+                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream,
+                 const float* head_gamma, int norm_cols) {
   using namespace g2;
   const bool dual = out_bf16 && out_f32;
   Gemm2Params p{};
@@ -589,6 +623,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.ln_inv_dim = 1.0f / (float)K;
   p.ln_eps = ln_eps;
   p.col_s = col_s;
+  p.head_gamma = head_gamma;
+  p.norm_cols = norm_cols;
   p.feed_skip = g_gemm_feed_skip;
   p.l2_prefetch = g_gemm_l2_prefetch;
   p.stage_limit = g_gemm_stage_limit;
@@ -636,7 +672,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   if (tiles < clusters) clusters = tiles;
 #define B200_G2_LAUNCH(MODE, CTF) launch_gemm2_t<MODE, CTF>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream)
   constexpr int F_BIAS = B200VIT_EPI_BIAS, F_GELU = B200VIT_EPI_GELU, F_RES = B200VIT_EPI_RESIDUAL,
-                F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS;
+                F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS, F_HN = B200VIT_EPI_HEADNORM;
   // the flag combinations of a transformer block get their own instantiation, anything else the generic kernel
   if (dual) {
     if (flags == (F_BIAS | F_RES | F_STATS)) return B200_G2_LAUNCH(MODE_DUAL, F_BIAS | F_RES | F_STATS);
@@ -644,6 +680,11 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
     return B200_G2_LAUNCH(MODE_DUAL, -1);
   }
   if (out_f32) return B200_G2_LAUNCH(MODE_F32, -1);
+  if (flags & F_HN) {  // (only reached through b200vit_gemm_headnorm_bf16)
+    if (flags == (F_HN | F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_HN | F_FOLD | F_BIAS);
+    if (flags == F_HN) return B200_G2_LAUNCH(MODE_BF16, F_HN);
+    return B200_G2_LAUNCH(MODE_BF16, -1);
+  }
   if (flags == (F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_FOLD | F_BIAS);
   if (flags == (F_FOLD | F_BIAS | F_GELU)) return B200_G2_LAUNCH(MODE_BF16, F_FOLD | F_BIAS | F_GELU);
   if (flags == (F_BIAS | F_GELU)) return B200_G2_LAUNCH(MODE_BF16, F_BIAS | F_GELU);

@@ -44,11 +44,13 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
                    const float* resid);
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
                  const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
-                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream);
+                 const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream,
+                 const float* head_gamma = nullptr, int norm_cols = 0);
 void gemm_force_version(int v);
 void gemm2_set_feed_skip(int v);
 void gemm2_set_l2_prefetch(int v);
 void gemm2_set_stage_limit(int v);
+void attention_varlen_set_mode(int v);
 
 int num_sms();
 

@@ -427,41 +427,51 @@ extern "C" int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, 
 // ---------------------------------------------------------------------------------------------------------------
 namespace b200 {
 
+// buf[T, ld] bf16: the `nheads` consecutive 64-wide heads starting at the row's column 0 are normalised in place.
+// One warp per token; 8 lanes per head (8 bf16 = 16 B each), so four heads are normalised per step with a 3-step
+// butterfly inside each 8-lane group; the loads of U steps are issued before the first reduction (a serial
+// load -> shuffle -> store chain per step left the kernel latency bound at a quarter of the HBM rate).
+template <int U>
 __global__ void __launch_bounds__(256)
-qk_rmsnorm_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ gamma_qk, int T, int H) {
-  // one warp per token; 8 lanes per head (8 bf16 = 16 B each), so four heads are normalised per step with a
-  // 3-step butterfly inside each 8-lane group
+rmsnorm_heads_kernel(__nv_bfloat16* __restrict__ buf, long long ld, const float* __restrict__ gamma, int T,
+                     int nheads) {
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
-  const int I = H * 64;
-  __nv_bfloat16* row = qkv + t * 3 * I;
-  const int sub = lane & 7;
-  for (int base = 0; base < 2 * H; base += 4) {  // q heads then k heads: the first 2*I columns of the row
-    const int hh = base + (lane >> 3);
-    const bool act = hh < 2 * H;               // (2H not a multiple of 4: the tail groups only join the shuffles)
-    uint4* vp = reinterpret_cast<uint4*>(row + (act ? hh : 0) * 64) + sub;
-    uint4 raw = *vp;
-    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
-    float2 f[4];
-    float ss = 0.f;
+  __nv_bfloat16* row = buf + t * ld;
+  const int sub = lane & 7, grp = lane >> 3;
+  for (int base = 0; base < nheads; base += 4 * U) {
+    uint4 raw[U];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[i] = __bfloat1622float2(h2[i]);
-      ss = fmaf(f[i].x, f[i].x, fmaf(f[i].y, f[i].y, ss));
+    for (int u = 0; u < U; ++u) {
+      const int hh = base + 4 * u + grp;  // (heads beyond nheads: the group only joins the shuffles)
+      raw[u] = *(reinterpret_cast<const uint4*>(row + (hh < nheads ? hh : 0) * 64) + sub);
     }
-    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
-    if (!act) continue;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma_qk + hh * 64 + 8 * sub);
-    const float4 g1 = *reinterpret_cast<const float4*>(gamma_qk + hh * 64 + 8 * sub + 4);
-    h2[0] = __floats2bfloat162_rn(f[0].x * inv * g0.x, f[0].y * inv * g0.y);
-    h2[1] = __floats2bfloat162_rn(f[1].x * inv * g0.z, f[1].y * inv * g0.w);
-    h2[2] = __floats2bfloat162_rn(f[2].x * inv * g1.x, f[2].y * inv * g1.y);
-    h2[3] = __floats2bfloat162_rn(f[3].x * inv * g1.z, f[3].y * inv * g1.w);
-    *vp = raw;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int hh = base + 4 * u + grp;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw[u]);
+      float2 f[4];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[i] = __bfloat1622float2(h2[i]);
+        ss = fmaf(f[i].x, f[i].x, fmaf(f[i].y, f[i].y, ss));
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
+      if (hh < nheads) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + hh * 64 + 8 * sub);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma + hh * 64 + 8 * sub + 4);
+        h2[0] = __floats2bfloat162_rn(f[0].x * inv * g0.x, f[0].y * inv * g0.y);
+        h2[1] = __floats2bfloat162_rn(f[1].x * inv * g0.z, f[1].y * inv * g0.w);
+        h2[2] = __floats2bfloat162_rn(f[2].x * inv * g1.x, f[2].y * inv * g1.y);
+        h2[3] = __floats2bfloat162_rn(f[3].x * inv * g1.z, f[3].y * inv * g1.w);
+        *(reinterpret_cast<uint4*>(row + hh * 64) + sub) = raw[u];
+      }
+    }
   }
 }
 
@@ -478,7 +488,38 @@ attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__
   const int I = H * 64;
   const float2 q = *reinterpret_cast<const float2*>(qn + h * 64 + 2 * lane);
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-  for (int j = cu[s]; j < cu[s + 1]; ++j) {
+  const int j1 = cu[s + 1];
+  int j = cu[s];
+  // four tokens per step: eight independent loads and four interleaved butterflies, one rescale of the running sums
+  for (; j + 4 <= j1; j += 4) {
+    float2 k[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16* r = kv + (long long)(j + i) * 2 * I + h * 64;
+      k[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r) + lane));
+      v[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r + I) + lane));
+    }
+    float sc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc[i] = q.x * k[i].x + q.y * k[i].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
+    }
+    const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+    const float corr = __expf(m - mn);
+    l *= corr; a0 *= corr; a1 *= corr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float pj = __expf(sc[i] - mn);
+      l += pj;
+      a0 = fmaf(pj, v[i].x, a0);
+      a1 = fmaf(pj, v[i].y, a1);
+    }
+    m = mn;
+  }
+  for (; j < j1; ++j) {
     const __nv_bfloat16* r = kv + (long long)j * 2 * I + h * 64;
     const float2 k = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r) + lane));
     const float2 v = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r + I) + lane));
@@ -494,15 +535,96 @@ attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__
   *(reinterpret_cast<__nv_bfloat162*>(out + (long long)s * I + h * 64) + lane) = __floats2bfloat162_rn(a0 * inv, a1 * inv);
 }
 
+// NaViT token assembly for packed variable-size images (reference na_vit.py:228,350-359): LayerNorm(dim, no bias) of
+// the patch projection + factorised positional embedding pos_h[row] + pos_w[col] of the token's place in ITS image's
+// patch grid -> fp32 residual stream, and (LN-fold entry) the bf16 copy + row statistics of it.  One warp per token;
+// the image of a token is found by bisection of cu_seqlens, its grid width is dims[s][1] / p.
+__global__ void __launch_bounds__(256)
+embed_varlen_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ pos_h,
+                    const float* __restrict__ pos_w, const int* __restrict__ cu, const int* __restrict__ dims,
+                    float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int T, int D,
+                    int S, int p, float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  int lo = 0, hi = S;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cu[mid] <= row) lo = mid; else hi = mid;
+  }
+  const int local = (int)row - cu[lo];
+  const int gw = dims[2 * lo + 1] / p;
+  const float* ph = pos_h + (long long)(local / gw) * D;
+  const float* pw = pos_w + (long long)(local % gw) * D;
+  const float* yr = y + row * D;
+  float* xr = x + row * D;
+  __nv_bfloat16* xbr = xb ? xb + row * D : nullptr;
+  float mean, rstd;
+  ln_row_stats(yr, D, lane, mean, rstd, eps);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {  // D % 4 == 0 (checked by the launcher)
+    const float4 v = *reinterpret_cast<const float4*>(yr + i);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+    const float4 a = *reinterpret_cast<const float4*>(ph + i);
+    const float4 b = *reinterpret_cast<const float4*>(pw + i);
+    float4 o;  // same association as the reference: (LN + pos_h) + pos_w
+    o.x = ((v.x - mean) * rstd * g.x + a.x) + b.x;
+    o.y = ((v.y - mean) * rstd * g.y + a.y) + b.y;
+    o.z = ((v.z - mean) * rstd * g.z + a.z) + b.z;
+    o.w = ((v.w - mean) * rstd * g.w + a.w) + b.w;
+    *reinterpret_cast<float4*>(xr + i) = o;
+    uint2 pk;
+    pk.x = pack_bf16x2(o.x, o.y);
+    pk.y = pack_bf16x2(o.z, o.w);
+    if (xbr) *reinterpret_cast<uint2*>(xbr + i) = pk;
+    const float a0 = __uint_as_float(pk.x << 16), a1 = __uint_as_float(pk.x & 0xFFFF0000u);
+    const float a2 = __uint_as_float(pk.y << 16), a3 = __uint_as_float(pk.y & 0xFFFF0000u);
+    s1 += (a0 + a1) + (a2 + a3);
+    s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+  }
+  if (stats) {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      stats[2 * row] = s1;
+      stats[2 * row + 1] = s2;
+    }
+  }
+}
+
 }  // namespace b200
+
+extern "C" int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh,
+                                     void* stream) {
+  B200_CHECK_ARG(buf && gamma && T > 0 && nheads > 0, "rmsnorm_heads: bad argument");
+  B200_CHECK_ARG(dh == 64, "rmsnorm_heads: dim_head=%d not supported by this build (only 64)", dh);
+  B200_CHECK_ARG(ld >= (int64_t)nheads * 64 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
+                 "rmsnorm_heads: rows must be 16-byte aligned and hold nheads*64 columns (ld=%lld)", (long long)ld);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto b = reinterpret_cast<__nv_bfloat16*>(buf);
+  if (nheads > 8) b200::rmsnorm_heads_kernel<4><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads);
+  else b200::rmsnorm_heads_kernel<2><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads);
+  B200_CHECK_CUDA(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}
 
 extern "C" int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H, int dh, void* stream) {
   B200_CHECK_ARG(qkv && gamma_qk && T > 0 && H > 0, "qk_rmsnorm: bad argument");
   B200_CHECK_ARG(dh == 64, "qk_rmsnorm: dim_head=%d not supported by this build (only 64)", dh);
-  qk_rmsnorm_kernel<<<(T + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(qkv), gamma_qk, T, H);
+  return b200vit_rmsnorm_heads(qkv, (int64_t)3 * H * 64, gamma_qk, T, 2 * H, dh, stream);  // q heads, then k heads
+}
+
+extern "C" int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h, const float* pos_w,
+                                    const int32_t* cu_seqlens_dev, const int32_t* dims_dev, float* x, void* xb_bf16,
+                                    float* stats, int T, int D, int S, int p, float eps, void* stream) {
+  B200_CHECK_ARG(y && gamma && pos_h && pos_w && cu_seqlens_dev && dims_dev && x, "embed_varlen: null pointer");
+  B200_CHECK_ARG(T > 0 && S > 0 && p > 0 && D > 0 && (D % 4) == 0, "embed_varlen: bad shape T=%d D=%d S=%d", T, D, S);
+  b200::embed_varlen_kernel<<<(T + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y, gamma, pos_h, pos_w, cu_seqlens_dev, dims_dev, x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, T, D, S, p,
+      eps);
   B200_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  b200::count_launch();
   return 0;
 }
 
@@ -574,6 +696,103 @@ patchify_varlen_ln_kernel(const long long* __restrict__ img_ptrs, const int* __r
   }
 }
 
+// p == 16 fast path (C <= 4, out rows 16-byte aligned): the slab rows are padded by 16 bytes so that the 16-byte chunk
+// reads of a patch (row stride W*2 bytes, often a multiple of 512) do not collide on banks; every lane owns C chunks of
+// 8 pixels = one 16-byte piece of the output row, so the patch is read once, normalised in registers and written with
+// fully coalesced 16-byte stores.  Images whose base is 16-byte aligned and whose width is a multiple of 8 are staged
+// with 16-byte loads, others element by element.
+__global__ void __launch_bounds__(256)
+patchify_varlen_ln16_kernel(const long long* __restrict__ img_ptrs, const int* __restrict__ dims,
+                            const int* __restrict__ cu, const int* __restrict__ row_prefix,
+                            const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out, long long ldo, int S,
+                            int C, int wp, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [C*16][wp]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_rows = row_prefix[S];
+  const int pd = C * 256;
+  const float inv_pd = 1.0f / (float)pd;
+  for (int r = blockIdx.x; r < total_rows; r += gridDim.x) {
+    int lo = 0, hi = S;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_prefix[mid] <= r) lo = mid; else hi = mid;
+    }
+    const int s = lo, h = r - row_prefix[s];
+    const int H = dims[2 * s], W = dims[2 * s + 1];
+    const int gw = W >> 4;
+    const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(img_ptrs[s]);
+    __syncthreads();  // previous slab fully consumed
+    if (((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
+      const int vpr = W >> 3;
+      for (int i = threadIdx.x; i < C * 16 * vpr; i += blockDim.x) {
+        const int rowi = i / vpr, vx = i - rowi * vpr;
+        const int c = rowi >> 4, p1 = rowi & 15;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((long long)c * H + h * 16 + p1) * W) + vx);
+        *(reinterpret_cast<uint4*>(slab + (long long)rowi * wp) + vx) = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < C * 16 * W; i += blockDim.x) {
+        const int rowi = i / W, xx = i - rowi * W;
+        const int c = rowi >> 4, p1 = rowi & 15;
+        slab[(long long)rowi * wp + xx] = img[((long long)c * H + h * 16 + p1) * W + xx];
+      }
+    }
+    __syncthreads();
+    for (int w = warp; w < gw; w += 8) {
+      uint4 raw[4];
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < C) {
+          const int j = lane + 32 * k;  // 16-byte chunk j of the patch: slab row j/2, half j%2
+          raw[k] = *reinterpret_cast<const uint4*>(slab + (long long)(j >> 1) * wp + w * 16 + (j & 1) * 8);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+            sum += f.x + f.y;
+          }
+        }
+      }
+      const float mean = warp_sum(sum) * inv_pd;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < C) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+            const float a = f.x - mean, b = f.y - mean;
+            q = fmaf(a, a, fmaf(b, b, q));
+          }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_pd + eps);
+      __nv_bfloat16* orow = out + ((long long)cu[s] + (long long)h * gw + w) * ldo;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < C) {
+          const int j = lane + 32 * k;
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
+          const float4 g0 = *reinterpret_cast<const float4*>(gamma + j * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(gamma + j * 8 + 4);
+          const float2 f0 = __bfloat1622float2(h2[0]), f1 = __bfloat1622float2(h2[1]);
+          const float2 f2 = __bfloat1622float2(h2[2]), f3 = __bfloat1622float2(h2[3]);
+          uint4 pk;
+          pk.x = pack_bf16x2((f0.x - mean) * rstd * g0.x, (f0.y - mean) * rstd * g0.y);
+          pk.y = pack_bf16x2((f1.x - mean) * rstd * g0.z, (f1.y - mean) * rstd * g0.w);
+          pk.z = pack_bf16x2((f2.x - mean) * rstd * g1.x, (f2.y - mean) * rstd * g1.y);
+          pk.w = pack_bf16x2((f3.x - mean) * rstd * g1.z, (f3.y - mean) * rstd * g1.w);
+          *reinterpret_cast<uint4*>(orow + j * 8) = pk;
+        }
+      }
+      for (int e = pd + lane; e < (int)ldo; e += 32) orow[e] = __float2bfloat16_rn(0.f);  // K padding of the GEMM operand
+    }
+  }
+}
+
 }  // namespace b200
 
 extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int32_t* dims_dev,
@@ -584,22 +803,34 @@ extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int
                  "patchify_varlen_ln: null pointer");
   B200_CHECK_ARG(S > 0 && total_rows > 0 && C > 0 && p > 0 && max_w >= p, "patchify_varlen_ln: bad shape");
   B200_CHECK_ARG(ldo >= (int64_t)C * p * p, "patchify_varlen_ln: ldo too small");
-  const size_t smem = (size_t)C * p * max_w * 2;
+  const bool fast = p == 16 && C <= 4 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0;
+  const int wp = (max_w + 7) / 8 * 8 + 8;  // fast path: slab row stride in pixels (16 bytes of padding)
+  const size_t smem = fast ? (size_t)C * 16 * wp * 2 : (size_t)C * p * max_w * 2;
   B200_CHECK_ARG(smem <= 200 * 1024, "patchify_varlen_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-    smem_set = smem;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > smem_set[fast]) {
+    if (fast)
+      B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln16_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[fast] = smem;
   }
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   int grid = b200::num_sms() * per_sm;
   if (grid > total_rows) grid = total_rows;
-  b200::patchify_varlen_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(img_ptrs_dev), dims_dev, cu_seqlens_dev, row_prefix_dev, gamma,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, S, C, p, eps);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (fast)
+    b200::patchify_varlen_ln16_kernel<<<grid, 256, smem, st>>>(
+        reinterpret_cast<const long long*>(img_ptrs_dev), dims_dev, cu_seqlens_dev, row_prefix_dev, gamma,
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, S, C, wp, eps);
+  else
+    b200::patchify_varlen_ln_kernel<<<grid, 256, smem, st>>>(
+        reinterpret_cast<const long long*>(img_ptrs_dev), dims_dev, cu_seqlens_dev, row_prefix_dev, gamma,
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, S, C, p, eps);
   B200_CHECK_CUDA(cudaGetLastError());
   b200::count_launch();
   return 0;

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import _lib
-from .engine import hooks_inside, why_not_fused
+from .engine import hooks_inside, ln_mode, why_not_fused
 
 
 def group_images_by_max_seq_len(images: Sequence[Tensor], patch_size: int,
@@ -204,11 +204,21 @@ class NaViT(nn.Module):
             t[prefix + "ln"] = f32(a.norm.gamma)
             t[prefix + "qkv"] = bf(torch.cat([a.to_q.weight, a.to_kv.weight], dim=0))       # rows: q | k | v
             t[prefix + "kv"] = bf(a.to_kv.weight)
-            t[prefix + "gqk"] = torch.stack([f32(a.q_norm.gamma).reshape(-1), f32(a.k_norm.gamma).reshape(-1)]).contiguous()
+            t[prefix + "gqk"] = torch.cat([f32(a.q_norm.gamma).reshape(-1), f32(a.k_norm.gamma).reshape(-1)]).contiguous()
+            t[prefix + "gk"] = f32(a.k_norm.gamma).reshape(-1).contiguous()
             t[prefix + "out"] = bf(a.to_out[0].weight)
+
+        def fold(name: str, w: Tensor, gamma: Tensor) -> None:
+            # LN(x; gamma, beta = 0) W^T == rstd * (x (gamma * W)^T - mu * colsum): see engine.TransformerEngine
+            wg = (w.detach().float() * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+            t[name + "g"] = wg
+            t[name + "s"] = wg.float().sum(dim=1).contiguous()       # from the ROUNDED weights the MMA sees
 
         for i, (attn, ff) in enumerate(self.transformer.layers):
             attn_w(f"{i}.a.", attn)
+            fold(f"{i}.a.qkv", torch.cat([attn.to_q.weight, attn.to_kv.weight], dim=0), attn.norm.gamma)
+            t[f"{i}.a.qkvt"] = torch.zeros(t[f"{i}.a.qkvs"].shape[0], device=t[f"{i}.a.qkvs"].device)
+            fold(f"{i}.f.w1", ff[1].weight, ff[0].gamma)
             t[f"{i}.f.ln"] = f32(ff[0].gamma)
             t[f"{i}.f.w1"], t[f"{i}.f.b1"] = bf(ff[1].weight), f32(ff[1].bias)
             t[f"{i}.f.w2"], t[f"{i}.f.b2"] = bf(ff[4].weight), f32(ff[4].bias)
@@ -237,59 +247,62 @@ class NaViT(nn.Module):
         heads = self.attn_pool.heads
         D = t["pos_h"].shape[1]
         I = t["0.a.out"].shape[1]
-        # ---- host-side bookkeeping only: per-image token counts -> cu_seqlens; patch pixels are gathered on the GPU
-        lengths, gws = [], []
         for img in images:
             assert img.ndim == 3 and img.shape[0] == c
             hh, ww = img.shape[-2:]
             assert hh % p == 0 and ww % p == 0, f'height and width {(hh, ww)} of images must be divisible by patch size {p}'
-            lengths.append((hh // p) * (ww // p))
-            gws.append(ww // p)
         images = [im.contiguous() for im in images]
-        S = len(images)
-        T = sum(lengths)
-        cu, tile_prefix, total_tiles = _lib.varlen_index(lengths, dev)
-        # token -> (row, column) in its image's patch grid, vectorised (factorised positional tables, na_vit.py:354-359)
-        lens_t = torch.tensor(lengths, device=dev)
-        img_of = torch.repeat_interleave(torch.arange(S, device=dev), lens_t)
-        local = torch.arange(T, device=dev) - cu[:-1].long()[img_of]
-        gw_t = torch.tensor(gws, device=dev)[img_of]
-        h_idx, w_idx = local // gw_t, local % gw_t
+        # ---- host-side bookkeeping only: per-image token counts / grid shapes -> one small index buffer on the device;
+        #      patch pixels and positional rows are gathered by the kernels
+        ix = _lib.VarlenIndex(images, p, dev)
+        S, T = ix.S, ix.T
         bf16 = dict(device=dev, dtype=torch.bfloat16)
-        # ---- patch embedding: patchify + LN(no bias) -> Linear -> LN(no bias) -> + pos_h + pos_w  (na_vit.py:300,350-359)
+        f32 = dict(device=dev, dtype=torch.float32)
+        fold = ln_mode() == "fold"
+        # ---- patch embedding: patchify + LN(no bias) -> Linear -> LN(no bias) + pos_h + pos_w   (na_vit.py:300,350-359)
         pd = c * p * p
         a0 = torch.empty(T, pd, **bf16)
-        _lib.patchify_varlen_ln(images, t["pe.ln1"], a0, cu, p)
-        y = torch.empty(T, D, device=dev, dtype=torch.float32)
+        _lib.patchify_varlen_ln(images, t["pe.ln1"], a0, ix.cu, p, index=ix)
+        y = torch.empty(T, D, **f32)
         _lib.gemm(a0, t["pe.w"], out_f32=y, bias=t["pe.b"])
         x = torch.empty_like(y)
-        _lib.layernorm(y, t["pe.ln2"], None, out_f32=x)
-        x += t["pos_h"][h_idx]
-        x += t["pos_w"][w_idx]
+        xn = torch.empty(T, D, **bf16)              # exact: LayerNorm output; fold: bf16 copy of the residual stream
+        st_in = torch.empty(T, 1, 2, **f32) if fold else None
+        _lib.embed_varlen(y, t["pe.ln2"], t["pos_h"], t["pos_w"], ix, x, p, xb=xn if fold else None, stats=st_in)
         # ---- encoder layers on the packed [T, D] matrix                                     (na_vit.py:183-193)
-        xn = torch.empty(T, D, **bf16)
         qkv = torch.empty(T, 3 * I, **bf16)
         o = torch.empty(T, I, **bf16)
         hbuf = torch.empty(T, t["0.f.w1"].shape[0], **bf16)
-        for i in range(len(self.transformer.layers)):
-            _lib.layernorm(x, t[f"{i}.a.ln"], None, out_bf16=xn)
-            _lib.gemm(xn, t[f"{i}.a.qkv"], out_bf16=qkv)
-            _lib.qk_rmsnorm(qkv, t[f"{i}.a.gqk"], heads, 64)
-            _lib.attention_varlen(qkv, o, cu, tile_prefix, total_tiles, heads, 64, 1.0)
-            _lib.gemm(o, t[f"{i}.a.out"], out_f32=x, resid=x)
-            _lib.layernorm(x, t[f"{i}.f.ln"], None, out_bf16=xn)
-            _lib.gemm(xn, t[f"{i}.f.w1"], out_bf16=hbuf, bias=t[f"{i}.f.b1"], gelu=True)
-            _lib.gemm(hbuf, t[f"{i}.f.w2"], out_f32=x, bias=t[f"{i}.f.b2"], resid=x)
+        depth = len(self.transformer.layers)
+        if fold:
+            # LayerNorm folded into the QKV / FC1 GEMMs (engine.py): the residual GEMMs emit the bf16 copy of x and
+            # the partial row statistics the next folded GEMM needs
+            parts = _lib.stats_parts(D)
+            sa, sb = torch.empty(T, parts, 2, **f32), torch.empty(T, parts, 2, **f32)
+            for i in range(depth):
+                _lib.gemm_headnorm(xn, t[f"{i}.a.qkvg"], out_bf16=qkv, bias=t[f"{i}.a.qkvt"],
+                                   ln_sums=st_in if i == 0 else sa, col_s=t[f"{i}.a.qkvs"],
+                                   head_gamma=t[f"{i}.a.gqk"], norm_heads=2 * heads)   # q / k RMSNorm in the epilogue
+                _lib.attention_varlen(qkv, o, ix.cu, ix.tile_prefix, ix.total_tiles, heads, 64, 1.0)
+                _lib.gemm(o, t[f"{i}.a.out"], out_f32=x, out_bf16=xn, resid=x, stats_out=sb)
+                _lib.gemm(xn, t[f"{i}.f.w1g"], out_bf16=hbuf, bias=t[f"{i}.f.b1"], gelu=True, ln_sums=sb,
+                          col_s=t[f"{i}.f.w1s"])
+                _lib.gemm(hbuf, t[f"{i}.f.w2"], out_f32=x, out_bf16=xn, bias=t[f"{i}.f.b2"], resid=x, stats_out=sa)
+        else:
+            for i in range(depth):
+                _lib.layernorm(x, t[f"{i}.a.ln"], None, out_bf16=xn)
+                _lib.gemm_headnorm(xn, t[f"{i}.a.qkv"], out_bf16=qkv, head_gamma=t[f"{i}.a.gqk"], norm_heads=2 * heads)
+                _lib.attention_varlen(qkv, o, ix.cu, ix.tile_prefix, ix.total_tiles, heads, 64, 1.0)
+                _lib.gemm(o, t[f"{i}.a.out"], out_f32=x, resid=x)
+                _lib.layernorm(x, t[f"{i}.f.ln"], None, out_bf16=xn)
+                _lib.gemm(xn, t[f"{i}.f.w1"], out_bf16=hbuf, bias=t[f"{i}.f.b1"], gelu=True)
+                _lib.gemm(hbuf, t[f"{i}.f.w2"], out_f32=x, bias=t[f"{i}.f.b2"], resid=x)
         _lib.layernorm(x, t["norm"], None, out_bf16=xn)
         # ---- attention pooling: one query per image over that image's (un-normalised-again) tokens (na_vit.py:371-387)
         kv = torch.empty(T, 2 * I, **bf16)
-        _lib.gemm(xn, t["pool.kv"], out_bf16=kv)
-        kq = torch.empty(T, 3 * I, **bf16)          # qk_rmsnorm works on a [q | k | v] buffer: place k, v at 1/3, 2/3
-        kq[:, I:] = kv
-        kq[:, :I] = 0
-        _lib.qk_rmsnorm(kq, t["pool.gqk"], heads, 64)
+        _lib.gemm_headnorm(xn, t["pool.kv"], out_bf16=kv, head_gamma=t["pool.gk"], norm_heads=heads)   # k half only
         pooled = torch.empty(S, I, **bf16)
-        _lib.attn_pool(kq[:, I:].contiguous(), t["pool.qn"], cu, pooled, heads, 64)
+        _lib.attn_pool(kv, t["pool.qn"], ix.cu, pooled, heads, 64)
         z = t["pool.queries"][None, :].expand(S, -1).contiguous()
         _lib.gemm(pooled, t["pool.out"], out_f32=z, resid=z)                      # + queries
         zl = torch.empty(S, D, **bf16)
