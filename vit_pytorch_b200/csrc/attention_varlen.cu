@@ -38,6 +38,7 @@ struct AttnVarlenParams {
   int units;               // total_tiles * H
   float scale_log2e;
   __nv_bfloat16* out;
+  long long* trace;        // timing experiment (pipelined kernel, TRACE instantiation): [unit][16] stamps of CTA 0
 };
 
 __device__ __forceinline__ void av_locate(const AttnVarlenParams& p, int unit, int& seq, int& h, int& qt, int& row0,
@@ -314,10 +315,15 @@ constexpr int THREADS = 6 * 32;
 __device__ __forceinline__ uint32_t buf_col(int bf) { return bf == 2 ? 192u : static_cast<uint32_t>(bf) * KB; }
 }  // namespace av2
 
+template <bool TRACE>
 __global__ void __launch_bounds__(av2::THREADS, 2)
 attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const AttnVarlenParams p) {
   using namespace av2;
+  // %globaltimer stamp of slot `slot` of this CTA's `it`-th unit (CTA 0 only, first 64 units)
+  auto stamp = [&](uint32_t it, int slot) {
+    if (TRACE && blockIdx.x == 0 && it < 64) p.trace[it * 16 + slot] = (long long)globaltimer_ns();
+  };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -373,9 +379,11 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint32_t units_done = 0, kv_count = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
         int seq, h, qt, row0, n;
+        stamp(units_done, 12);
         av_locate(p, u, seq, h, qt, row0, n);
         const int nb = (n + KB - 1) / KB;
         mbar_wait(q_empty, (units_done & 1) ^ 1);
+        stamp(units_done, 13);
         mbar_arrive_expect_tx(q_full, Q_BYTES);
         tma_load_2d(sQ, &tmQ, q_full, h * DH, row0 + qt * 128);
         const int steps = (nb > 1 ? nb : 0) + nb;
@@ -409,7 +417,9 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         av_locate(p, u, seq, h, qt, row0, n);
         const int nb = (n + KB - 1) / KB;
         const int steps = (nb > 1 ? nb : 0) + nb;
+        stamp(units_done, 8);
         mbar_wait(q_full, units_done & 1);
+        stamp(units_done, 9);
         const uint32_t sc0 = sc;
         // issue Q K_b^T of step s (global step sc0 + s) into the next score buffer
         auto issue_s = [&](int s) {
@@ -441,6 +451,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
         };
         for (int s = 0; s < LOOKAHEAD && s < steps; ++s) issue_s(s);
+        stamp(units_done, 10);
         for (int s = 0; s < steps; ++s) {
           if (s + LOOKAHEAD < steps) issue_s(s + LOOKAHEAD);  // ahead of the softmax warps
           const int bf = bf_fin;
@@ -466,6 +477,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (kb == nb - 1) umma_commit(o_full);
         }
         sc = sc0 + steps;
+        stamp(units_done, 11);
       }
     }
   } else {
@@ -481,9 +493,15 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       bf = bf == NBUF - 1 ? 0 : bf + 1;
     };
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
+      const bool tr0 = TRACE && warp == 0 && lane == 0;
+      if (tr0) stamp(units_done, 0);
       int seq, h, qt, row0, n;
       av_locate(p, u, seq, h, qt, row0, n);
       const int nb = (n + KB - 1) / KB;
+      if (tr0) {
+        stamp(units_done, 1);
+        if (blockIdx.x == 0 && units_done < 64) p.trace[units_done * 16 + 7] = nb;
+      }
       const int qrow = qt * 128 + quad * 32 + lane;
       float mx = -INFINITY;
       auto block_max = [&](int kb, uint32_t tb) {
@@ -502,6 +520,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (nb > 1) {
         for (int kb = 0; kb < nb; ++kb) {
           mbar_wait(&s_full[bf], (par_sfull >> bf) & 1);
+          if (tr0 && kb == 0) stamp(units_done, 2);
           tc_fence_after();
           block_max(kb, t_lane + buf_col(bf));
           tc_fence_before();
@@ -511,9 +530,11 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       float sum = 0.f;
+      if (tr0) stamp(units_done, 3);
       for (int kb = 0; kb < nb; ++kb) {
         const uint32_t tb = t_lane + buf_col(bf);
         mbar_wait(&s_full[bf], (par_sfull >> bf) & 1);
+        if (tr0 && kb == 0) stamp(units_done, 4);
         tc_fence_after();
         if (nb == 1) block_max(0, tb);
         const float mc = mx * c;
@@ -542,7 +563,9 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         next_buf();
       }
       // epilogue: O / sum -> bf16 -> global
+      if (tr0) stamp(units_done, 5);
       mbar_wait(o_full, units_done & 1);
+      if (tr0) stamp(units_done, 6);
       tc_fence_after();
       const float inv = 1.0f / sum;
       uint32_t ob[32];
@@ -563,6 +586,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
+      if (tr0) stamp(units_done, 14);
     }
   }
 
@@ -574,6 +598,8 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
 }
 
+static long long* g_varlen_trace = nullptr;
+void attention_varlen_set_trace(long long* buf) { g_varlen_trace = buf; }
 static int g_varlen_mode = 0;  // 0: pipelined 64-key blocks (default), 1: the serial 128-key-block kernel
 void attention_varlen_set_mode(int v) { g_varlen_mode = v; }
 
@@ -613,11 +639,15 @@ extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_
     if (rc) return rc;
     static bool attr2_set = false;
     if (!attr2_set) {
-      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           av2::DYN_BYTES));
+      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, av2::DYN_BYTES));
+      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, av2::DYN_BYTES));
       attr2_set = true;
     }
-    attention_varlen2_kernel<<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
+    p.trace = g_varlen_trace;
+    if (p.trace) attention_varlen2_kernel<true><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
+    else attention_varlen2_kernel<false><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
   } else {
     CUtensorMap tm;
     const uint32_t box[2] = {64, 128};

@@ -51,6 +51,7 @@ void gemm2_set_feed_skip(int v);
 void gemm2_set_l2_prefetch(int v);
 void gemm2_set_stage_limit(int v);
 void attention_varlen_set_mode(int v);
+void attention_varlen_set_trace(long long* buf);
 
 int num_sms();
 
