@@ -77,3 +77,22 @@ def test_same_seed_init_and_live_reference():
         got = b([imgs[:2], imgs[2:]])
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
     assert torch.allclose(NO.navit_forward(O.upcast(sa), kwargs, [imgs[:2], imgs[2:]]), want, rtol=1e-4, atol=1e-5)
+
+
+def test_varlen_index_arrays_host_logic():
+    """_lib.VarlenIndex: one packed buffer holds cu_seqlens / query-tile prefix / patch-row prefix / dims / addresses."""
+    from vit_pytorch_b200 import _lib
+    p = 16
+    sizes = [(48, 32), (16, 16), (512, 512), (64, 80), (2064, 16)]
+    imgs = [torch.zeros(3, h, w, dtype=torch.bfloat16) for h, w in sizes]
+    ix = _lib.VarlenIndex(imgs, p, "cpu")
+    lens = [(h // p) * (w // p) for h, w in sizes]
+    assert ix.S == len(sizes) and ix.T == sum(lens) and ix.lengths == lens
+    assert ix.cu.dtype == torch.int32 and ix.cu.tolist() == [0] + torch.tensor(lens).cumsum(0).tolist()
+    tiles = [(n + 127) // 128 for n in lens]
+    assert ix.tile_prefix.tolist() == [0] + torch.tensor(tiles).cumsum(0).tolist() and ix.total_tiles == sum(tiles)
+    rows = [h // p for h, _ in sizes]
+    assert ix.row_prefix.tolist() == [0] + torch.tensor(rows).cumsum(0).tolist() and ix.total_rows == sum(rows)
+    assert ix.dims.tolist() == [v for hw in sizes for v in hw] and ix.max_w == 512
+    assert ix.img_ptrs.dtype == torch.int64 and ix.img_ptrs.tolist() == [im.data_ptr() for im in imgs]
+    assert ix.cu.data_ptr() % 4 == 0 and ix.img_ptrs.data_ptr() % 8 == 0
