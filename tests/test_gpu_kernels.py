@@ -121,7 +121,8 @@ def test_layernorm_row_gather_no_bias():
     assert torch.allclose(of.cpu(), O.layer_norm(x[rows.long()].cpu(), g.cpu(), None), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("C,H,W,p", [(3, 224, 224, 16), (3, 32, 32, 4), (3, 224, 224, 14), (1, 64, 32, 8)])
+@pytest.mark.parametrize("C,H,W,p", [(3, 224, 224, 16), (3, 32, 32, 4), (3, 224, 224, 14), (1, 64, 32, 8),
+                                     (3, 384, 256, 16), (3, 48, 16, 16), (4, 32, 32, 16)])
 def test_patchify_ln(C, H, W, p):
     torch.manual_seed(5)
     img = torch.randn(3, C, H, W, device=DEV).bfloat16()
@@ -209,127 +210,6 @@ def test_gelu_epilogue_accuracy():
     ref = O.gelu_erf(xs.double().cpu())
     got = ob[5].double().cpu()
     assert ((got - ref).abs() <= 1.2e-5 + ref.abs() * 2.0 ** -8).all()
-
-
-@pytest.mark.parametrize("M,D", [(1000, 768), (77, 50), (513, 1280)])
-def test_layernorm(M, D):
-    torch.manual_seed(3)
-    x = torch.randn(M, D, device=DEV) * 3 + 1
-    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
-    of = torch.zeros(M, D, device=DEV)
-    ob = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
-    _lib.layernorm(x, g, b, out_bf16=ob, out_f32=of)
-    ref = O.layer_norm(x.cpu(), g.cpu(), b.cpu())
-    assert torch.allclose(of.cpu(), ref, rtol=1e-5, atol=1e-5)
-    assert torch.equal(ob.cpu(), of.cpu().bfloat16())
-
-
-def test_layernorm_row_gather_no_bias():
-    torch.manual_seed(4)
-    x = torch.randn(197 * 4, 256, device=DEV)
-    g = torch.randn(256, device=DEV)
-    rows = torch.arange(0, 197 * 4, 197, device=DEV, dtype=torch.int32)
-    of = torch.zeros(4, 256, device=DEV)
-    _lib.layernorm(x, g, None, out_f32=of, row_index=rows)
-    assert torch.allclose(of.cpu(), O.layer_norm(x[rows.long()].cpu(), g.cpu(), None), rtol=1e-5, atol=1e-5)
-
-
-@pytest.mark.parametrize("C,H,W,p", [(3, 224, 224, 16), (3, 32, 32, 4), (3, 224, 224, 14), (1, 64, 32, 8)])
-def test_patchify_ln(C, H, W, p):
-    torch.manual_seed(5)
-    img = torch.randn(3, C, H, W, device=DEV).bfloat16()
-    pd = C * p * p
-    ldo = (pd + 63) // 64 * 64
-    g, b = torch.randn(pd, device=DEV), torch.randn(pd, device=DEV)
-    out = torch.full((3 * (H // p) * (W // p), ldo), 7.0, device=DEV, dtype=torch.bfloat16)
-    _lib.patchify_ln(img, g, b, out, p, p)
-    ref = O.layer_norm(O.patchify(img.float().cpu(), p, p), g.cpu(), b.cpu()).reshape(-1, pd)
-    assert torch.equal(out[:, :pd].cpu(), ref.bfloat16()) or within(out[:, :pd], ref) > 0.9999
-    assert (out[:, pd:] == 0).all()
-
-
-@pytest.mark.parametrize("ncls", [0, 1])
-def test_embed_tokens(ncls):
-    torch.manual_seed(6)
-    B, n, D = 3, 49, 192
-    y = torch.randn(B * n, D, device=DEV)
-    g, be = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
-    cls = torch.randn(ncls, D, device=DEV) if ncls else None
-    pos = torch.randn(n + ncls, D, device=DEV)
-    x = torch.zeros(B * (n + ncls), D, device=DEV)
-    xb = torch.zeros(B * (n + ncls), D, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(B * (n + ncls), 1, 2, device=DEV)
-    _lib.embed_tokens(y, g, be, cls, pos, x, B, n, ncls, xb=xb, stats=st)
-    st = st[:, 0]
-    t = O.layer_norm(y.cpu(), g.cpu(), be.cpu()).view(B, n, D)
-    if ncls:
-        t = torch.cat([cls.cpu()[None].expand(B, -1, -1), t], 1)
-    assert torch.allclose(x.cpu(), (t + pos.cpu()[None]).reshape(-1, D), rtol=1e-5, atol=1e-5)
-    # bf16 copy and its row statistics (inputs of the first LN-folded GEMM)
-    assert torch.equal(xb, x.bfloat16())
-    xr = xb.float()
-    assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-5, atol=1e-3)
-    assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-5, atol=1e-3)
-
-
-def test_rowstats_cast():
-    torch.manual_seed(8)
-    x = torch.randn(333, 768, device=DEV) * 2 + 0.5
-    xb = torch.zeros(333, 768, device=DEV, dtype=torch.bfloat16)
-    st = torch.zeros(333, 1, 2, device=DEV)
-    _lib.rowstats_cast(x, xb, st)
-    st = st[:, 0]
-    assert torch.equal(xb, x.bfloat16())
-    xr = xb.float()
-    assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-5, atol=1e-3)
-    assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-5, atol=1e-3)
-
-
-@pytest.mark.parametrize("M,N,K", [(2048, 768, 768), (1300, 1024, 512)])
-def test_gemm_pair_kernel_dual_epilogue(M, N, K):
-    """CTA-pair kernel, LN-fold producer epilogue: fp32 stream in place + bf16 copy + row statistics."""
-    torch.manual_seed(M)
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
-    b = torch.randn(N, device=DEV)
-    x0 = torch.randn(M, N, device=DEV)
-    x = x0.clone()
-    xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    st = torch.full((M, _lib.stats_parts(N), 2), 123.0, device=DEV)          # every slot must be overwritten
-    _lib.gemm(a, w, out_f32=x, out_bf16=xb, bias=b, resid=x, stats_out=st)
-    st2 = st.clone()
-    x2 = x0.clone()
-    _lib.gemm(a, w, out_f32=x2, out_bf16=xb, bias=b, resid=x2, stats_out=st2)
-    assert torch.equal(st, st2) and torch.equal(x, x2)                        # deterministic, no atomics
-    st = st.sum(1)
-    ref = O.linear(a.float().cpu(), w.float().cpu(), b.cpu()) + x0.cpu()
-    assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
-    assert torch.equal(xb, x.bfloat16())
-    xr = xb.float()
-    assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-4, atol=2e-2)
-    assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-4, atol=2e-2)
-
-
-def test_gelu_epilogue_accuracy():
-    """The GELU in the GEMM epilogue is the erf definition to 1.2e-5 absolute (before bf16 rounding)."""
-    K, N = 64, 256
-    xs = torch.linspace(-8, 8, 4096 * 4, device=DEV)[: 4096 * 4 // N * N].view(-1, N)   # values to activate
-    M = xs.shape[0]
-    a = torch.zeros(M, K, device=DEV, dtype=torch.bfloat16)
-    w = torch.zeros(N, K, device=DEV, dtype=torch.bfloat16)                            # acc = 0, bias carries x
-    # per-column bias cannot carry a per-element value: use A = one-hot row scale instead
-    a[:, 0] = 1.0
-    out = torch.zeros(M, N, device=DEV)
-    for r in range(0, M, 64):                      # 64 rows at a time share a bias vector? no: drive through W
-        pass
-    w[:, 0] = 0
-    # simplest exact drive: A[m,0] = 1, W[n,0] = 0 and bias = x row -> identical rows; test row by row in chunks
-    for r in range(0, M, max(1, M // 8)):
-        ob = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-        _lib.gemm(a, w, out_bf16=ob, bias=xs[r].contiguous(), gelu=True)
-        ref = O.gelu_erf(xs[r].double().cpu())
-        got = ob[0].double().cpu()
-        assert (got - ref).abs().max() <= 1.2e-5 + ref.abs().max() * 2 ** -8
 
 
 @pytest.mark.parametrize("B,N,H", [(4, 197, 12), (3, 64, 3), (2, 257, 16), (5, 50, 4), (2, 16, 2), (2, 129, 2),

@@ -201,6 +201,88 @@ patchify_ln_kernel(const __nv_bfloat16* __restrict__ img, const float* __restric
   }  // persistent loop over (image, patch row)
 }
 
+// 16 x 16 patches, 3 channels, 16-byte aligned rows (W % 8 == 0): the ViT-B/L geometry.  Slab rows are padded so that
+// the 16-byte chunk reads of a patch are bank-conflict free (row stride = 16 bytes mod 64); lane (p1, half) reads 8
+// pixels of each channel, interleaves them to the 24 consecutive (p1 p2 c) outputs it owns and writes three 16-byte
+// pieces -- every patch is read from shared memory once with 128-bit loads and leaves as coalesced 48-byte runs.
+// gamma / beta are staged in shared memory once per (persistent) CTA.
+__global__ void __launch_bounds__(256)
+patchify_ln16c3_kernel(const __nv_bfloat16* __restrict__ img, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long ldo, int nrows,
+                       int H, int W, int wp, float eps) {
+  constexpr int C = 3, P = 16, PD = C * P * P;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* sg = reinterpret_cast<float*>(smem_raw);         // [768] gamma
+  float* sb = sg + PD;                                    // [768] beta
+  __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(sb + PD);  // [C*16][wp]
+  const int gh = H / P, gw = W / P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < PD; i += blockDim.x) {
+    sg[i] = gamma[i];
+    sb[i] = beta[i];
+  }
+  const int vpr = W >> 3;
+  const int p1 = lane >> 1, half = lane & 1;
+  const int e0 = (p1 * P + half * 8) * C;  // first of this lane's 24 output elements
+  for (int bh = blockIdx.x; bh < nrows; bh += gridDim.x) {
+    const int b = bh / gh, h = bh % gh;
+    __syncthreads();  // previous slab fully consumed (and gamma / beta staged)
+    for (int i = threadIdx.x; i < C * P * vpr; i += blockDim.x) {
+      const int rowi = i / vpr, vx = i - rowi * vpr;
+      const int c = rowi >> 4, r = rowi & 15;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((long long)(b * C + c) * H + h * P + r) * W) + vx);
+      *(reinterpret_cast<uint4*>(slab + (long long)rowi * wp) + vx) = v;
+    }
+    __syncthreads();
+    for (int w = warp; w < gw; w += 8) {
+      float f[C][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(slab + (long long)(c * P + p1) * wp + w * P + half * 8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __bfloat1622float2(h2[i]);
+          f[c][2 * i] = t.x;
+          f[c][2 * i + 1] = t.y;
+          sum += t.x + t.y;
+        }
+      }
+      const float mean = warp_sum(sum) * (1.0f / PD);
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[c][i] - mean;
+          q = fmaf(d, d, q);
+        }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / PD) + eps);
+      __nv_bfloat16* orow = out + ((long long)(b * gh + h) * gw + w) * ldo;
+      // outputs e0 + j, j = px*3 + c, in three groups of 8
+      float y[24];
+#pragma unroll
+      for (int px = 0; px < 8; ++px)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int j = px * C + c;
+          y[j] = (f[c][px] - mean) * rstd * sg[e0 + j] + sb[e0 + j];
+        }
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        uint4 pk;
+        pk.x = pack_bf16x2(y[8 * g], y[8 * g + 1]);
+        pk.y = pack_bf16x2(y[8 * g + 2], y[8 * g + 3]);
+        pk.z = pack_bf16x2(y[8 * g + 4], y[8 * g + 5]);
+        pk.w = pack_bf16x2(y[8 * g + 6], y[8 * g + 7]);
+        *reinterpret_cast<uint4*>(orow + e0 + 8 * g) = pk;
+      }
+      for (int e = PD + lane; e < (int)ldo; e += 32) orow[e] = __float2bfloat16_rn(0.f);  // K padding
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Token assembly: LN(dim) of the patch projection + positional embedding + cls row  -> fp32 residual stream
 // ---------------------------------------------------------------------------------------------------------------
@@ -359,20 +441,33 @@ extern "C" int b200vit_patchify_ln(const void* img, const float* gamma, const fl
   B200_CHECK_ARG(B > 0 && C > 0 && ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0,
                  "patchify_ln: image %dx%d not divisible by patch %dx%d", H, W, ph, pw);
   B200_CHECK_ARG(ldo >= (int64_t)C * ph * pw, "patchify_ln: ldo too small");
-  const size_t smem = (size_t)C * ph * W * 2;
+  const bool fast = C == 3 && ph == 16 && pw == 16 && (W % 8) == 0 && ((long long)H * W) % 8 == 0 && (ldo % 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0;
+  const int wp = (W + 31) / 32 * 32 + 16;  // fast path: padded slab row (stride = 16 bytes mod 64: no bank conflicts)
+  const size_t smem = fast ? (size_t)C * 16 * wp * 2 + 2 * 768 * sizeof(float) : (size_t)C * ph * W * 2;
   B200_CHECK_ARG(smem <= 200 * 1024, "patchify_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > smem_set[fast]) {
+    if (fast)
+      B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln16c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    else
+      B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[fast] = smem;
   }
   const int nrows = B * (H / ph);
   const int per_sm = (int)(200 * 1024 / (smem + 1024)) < 8 ? (int)(200 * 1024 / (smem + 1024)) : 8;
   int grid = num_sms() * (per_sm < 1 ? 1 : per_sm);
   if (grid > nrows) grid = nrows;
-  patchify_ln_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, nrows,
-      C, H, W, ph, pw, eps);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (fast)
+    patchify_ln16c3_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta,
+                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, nrows, H, W, wp,
+                                                    eps);
+  else
+    patchify_ln_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(img), gamma, beta,
+                                                reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, nrows, C, H, W, ph, pw,
+                                                eps);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -804,7 +899,7 @@ extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int
   B200_CHECK_ARG(S > 0 && total_rows > 0 && C > 0 && p > 0 && max_w >= p, "patchify_varlen_ln: bad shape");
   B200_CHECK_ARG(ldo >= (int64_t)C * p * p, "patchify_varlen_ln: ldo too small");
   const bool fast = p == 16 && C <= 4 && (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0;
-  const int wp = (max_w + 7) / 8 * 8 + 8;  // fast path: slab row stride in pixels (16 bytes of padding)
+  const int wp = (max_w + 31) / 32 * 32 + 16;  // fast path: slab row stride in pixels (= 16 bytes mod 64: no bank conflicts)
   const size_t smem = fast ? (size_t)C * 16 * wp * 2 : (size_t)C * p * max_w * 2;
   B200_CHECK_ARG(smem <= 200 * 1024, "patchify_varlen_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
   static size_t smem_set[2] = {0, 0};
