@@ -308,7 +308,8 @@ constexpr int LOOKAHEAD = 2;                 // Q K^T is issued this many steps 
 constexpr int SMEM_DATA = Q_BYTES + 2 * KV_BYTES * KV_STAGES;
 // q_full q_empty kv_full[4] kv_empty[4] s_full[3] s_free[3] p_ready[3] pv_done[3] o_full o_free
 constexpr int NUM_BARS = 2 + 2 * KV_STAGES + 4 * NBUF + 2;
-constexpr int DYN_BYTES = SMEM_DATA + NUM_BARS * 8 + 16 + 1024;
+constexpr int UNIT_TAB = 128;                // units of this CTA located once, in parallel, at kernel start
+constexpr int DYN_BYTES = SMEM_DATA + NUM_BARS * 8 + 16 + UNIT_TAB * 16 + 1024;
 constexpr int TMEM_COLS = 256;
 constexpr int O_COL = 128;
 constexpr int THREADS = 6 * 32;
@@ -340,10 +341,32 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* o_full = pv_done + NBUF;
   uint64_t* o_free = o_full + 1;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+  int4* unit_tab = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(bars) + NUM_BARS * 8 + 16);  // (seq, qt, row0, n)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int TMA_WARP = 4, MMA_WARP = 5;
+
+  // Every role needs (sequence, query tile, first row, length) of each unit; the bisection of tile_prefix costs
+  // ~0.6 us of dependent loads per unit and role, so the first UNIT_TAB units of this CTA are located here, one per
+  // thread, and read back from shared memory (units beyond the table fall back to the bisection).
+  for (int i = threadIdx.x; i < UNIT_TAB; i += blockDim.x) {
+    const long long u = (long long)blockIdx.x + (long long)i * gridDim.x;
+    if (u < p.units) {
+      int seq, h, qt, row0, n;
+      av_locate(p, (int)u, seq, h, qt, row0, n);
+      unit_tab[i] = make_int4(seq, qt, row0, n);
+    }
+  }
+  auto locate = [&](int u, uint32_t idx, int& seq, int& h, int& qt, int& row0, int& n) {
+    if (idx < (uint32_t)UNIT_TAB) {
+      const int4 e = unit_tab[idx];
+      seq = e.x; qt = e.y; row0 = e.z; n = e.w;
+      h = u % p.H;
+    } else {
+      av_locate(p, u, seq, h, qt, row0, n);
+    }
+  };
 
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -380,7 +403,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
         int seq, h, qt, row0, n;
         stamp(units_done, 12);
-        av_locate(p, u, seq, h, qt, row0, n);
+        locate(u, units_done, seq, h, qt, row0, n);
         const int nb = (n + KB - 1) / KB;
         mbar_wait(q_empty, (units_done & 1) ^ 1);
         stamp(units_done, 13);
@@ -414,7 +437,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       uint32_t owes_sfree = 0, owes_pv = 0;  // bit b: the buffer's last user still has to signal s_free / pv_done
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
         int seq, h, qt, row0, n;
-        av_locate(p, u, seq, h, qt, row0, n);
+        locate(u, units_done, seq, h, qt, row0, n);
         const int nb = (n + KB - 1) / KB;
         const int steps = (nb > 1 ? nb : 0) + nb;
         stamp(units_done, 8);
@@ -496,7 +519,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const bool tr0 = TRACE && warp == 0 && lane == 0;
       if (tr0) stamp(units_done, 0);
       int seq, h, qt, row0, n;
-      av_locate(p, u, seq, h, qt, row0, n);
+      locate(u, units_done, seq, h, qt, row0, n);
       const int nb = (n + KB - 1) / KB;
       if (tr0) {
         stamp(units_done, 1);
