@@ -96,3 +96,30 @@ def test_varlen_index_arrays_host_logic():
     assert ix.dims.tolist() == [v for hw in sizes for v in hw] and ix.max_w == 512
     assert ix.img_ptrs.dtype == torch.int64 and ix.img_ptrs.tolist() == [im.data_ptr() for im in imgs]
     assert ix.cu.data_ptr() % 4 == 0 and ix.img_ptrs.data_ptr() % 8 == 0
+
+
+def test_navit_lnfold_prepared_tensors_reproduce_layernorm_linear():
+    """Host side of the LN-fold (na_vit.py:_prepared): with W_g = W * gamma (bf16), s = rowsum(W_g) and the row
+    statistics of the bf16 token copy,  rstd * (xb W_g^T - mu * s) + t  equals  Linear(LayerNorm(x))  of the reference
+    modules (Attention.norm -> to_q / to_kv and FeedForward[0] -> [1], na_vit.py:142-146,105-113)."""
+    torch.manual_seed(0)
+    m = NaViT(image_size=64, patch_size=8, num_classes=5, dim=64, depth=2, heads=2, mlp_dim=128).eval()
+    with torch.no_grad():
+        for p in m.parameters():                      # non-trivial gammas
+            if p.ndim == 1:
+                p.add_(0.3 * torch.randn_like(p))
+    t = m._prepared()
+    x = torch.randn(37, 64) * 2 + 0.5
+    xb = x.bfloat16().float()
+    mu = xb.mean(1, keepdim=True)
+    rstd = torch.rsqrt((xb * xb).mean(1, keepdim=True) - mu * mu + 1e-5)
+    for i, (attn, ff) in enumerate(m.transformer.layers):
+        with torch.no_grad():
+            xn = attn.norm(xb)
+            want_qkv = torch.cat([attn.to_q(xn), attn.to_kv(xn)], dim=-1)
+            want_h = ff[1](ff[0](xb))
+        got_qkv = rstd * (xb @ t[f"{i}.a.qkvg"].float().t() - mu * t[f"{i}.a.qkvs"]) + t[f"{i}.a.qkvt"]
+        got_h = rstd * (xb @ t[f"{i}.f.w1g"].float().t() - mu * t[f"{i}.f.w1s"]) + t[f"{i}.f.b1"]
+        assert torch.allclose(got_qkv, want_qkv, rtol=2e-2, atol=2e-2), (got_qkv - want_qkv).abs().max()
+        assert torch.allclose(got_h, want_h, rtol=2e-2, atol=2e-2), (got_h - want_h).abs().max()
+        assert t[f"{i}.a.gqk"].numel() == 2 * 2 * 64 and t[f"{i}.a.qkvt"].abs().max() == 0
