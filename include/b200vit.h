@@ -9,7 +9,9 @@
  * Conventions
  *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
  *   - the caller owns every buffer (including workspaces); the library allocates nothing on the device.
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*) of the CURRENT device (the caller selects it,
+ *     the library never calls cudaSetDevice); no internal synchronisation.  Entry points are re-entrant; per-device
+ *     state (SM count, shared-memory attributes) is kept per device, tensor-map descriptors are cached per key.
  *   - return value 0 = success, negative = error; message via b200vit_last_error() (thread local).
  *   - bf16 = __nv_bfloat16 storage; accumulation, LayerNorm statistics, softmax and the residual stream are fp32.
  */
@@ -99,7 +101,8 @@ int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, in
  * Multi-head softmax attention straight out of the packed QKV buffer:
  *   qkv[B*N, 3*H*dh] bf16 (columns: [q | k | v], each head-major h*dh + d; vit.py:54-55)
  *   out[B*N, H*dh]   bf16 (merged heads, vit.py:63) = softmax(q k^T * scale) v          (vit.py:57-62)
- * One pass over the keys (N <= 256): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ * One pass over the keys (N <= 512): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ * N <= 224: software-pipelined kernel (attention_pipe.cu: two score regions + one O slot per SM, K/V once per head).
  */
 int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
 
@@ -155,10 +158,12 @@ int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int 
  * + pos_h[row of the token in its image's patch grid] + pos_w[column]; optional bf16 copy xb and stats[T][2] =
  * (sum, sum of squares) of that copy (entry statistics of the LN-folded layer chain, as b200vit_embed_tokens).
  * cu_seqlens_dev[S+1]; dims_dev[S][2] = (H_s, W_s) in pixels (grid width = W_s / p).  D multiple of 4.
+ * pos_h[pos_h_rows][D], pos_w[pos_w_rows][D]: every image's patch grid must fit the tables (the reference raises an
+ * index error otherwise, na_vit.py:354-359; the caller checks, the kernel additionally clamps the row index).
  */
-int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h, const float* pos_w,
-                         const int32_t* cu_seqlens_dev, const int32_t* dims_dev, float* x, void* xb_bf16,
-                         float* stats, int T, int D, int S, int p, float eps, void* stream);
+int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h, const float* pos_w, int pos_h_rows,
+                         int pos_w_rows, const int32_t* cu_seqlens_dev, const int32_t* dims_dev, float* x,
+                         void* xb_bf16, float* stats, int T, int D, int S, int p, float eps, void* stream);
 
 /*
  * NaViT attention pooling (na_vit.py:371-387): out[s, h*dh:(h+1)*dh] = softmax_j(qn_h . k_jh) v_jh over the tokens j of
@@ -173,18 +178,17 @@ int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* str
 /* fp32 -> bf16 cast of a contiguous buffer of n elements (n multiple of 8). */
 int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
 
-/* Experiment knobs for kernel bring-up (not part of the drop-in surface).
- * key 1: attention variant (0 = auto, 1 = one CTA per SM, 2 / 3 = 8 softmax warps per score tile); key 2/3: V descriptor
- * LBO / SBO bytes; key 7: FMA-pipe exp2 for 0 / 8 / 16 of every 32 softmax exponentials;
- * key 4: GEMM kernel choice (0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies);
- * key 5 / 6: attention timing experiments (skip the row-max pass -- NOT numerically safe; split the PV accumulation);
- * key 8: CTA-pair GEMM operand-feed probe (thin out / drop the TMA operand loads -- WRONG results, timing only);
- * key 9: CTA-pair GEMM: prefetch the A panel into L2 this many k blocks ahead (0 = off, the default);
- * key 10: CTA-pair GEMM: use only this many stages of the operand ring (0 = all);
- * key 11: varlen attention kernel (0 = pipelined 64-key blocks, the default; 1 = serial 128-key blocks).
- * Any attention knob selects a separately compiled debug instantiation; the production kernels carry no knob code. */
+/*
+ * TEST HOOKS -- process-global switches for A/B tests and bring-up; NOT part of the re-entrant API above (a value set
+ * here changes every later call of every thread).  Production code never calls them.
+ *   key 1: b200vit_attention kernel choice: 0 = auto (pipelined kernel for N <= 224), 1 = round-1 kernels only
+ *   key 2 / 3: V (MN-major) descriptor LBO / SBO bytes (bring-up probe)
+ *   key 4: GEMM kernel choice: 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies
+ *   key 11: varlen attention kernel: 0 = pipelined 64-key blocks (default), 1 = serial 128-key blocks
+ *   key 12: fp32-epilogue warps of the CTA-pair GEMM: 0 = auto (4 when K >= 2048, else 8), 4 / 8 = forced
+ */
 int b200vit_debug_set(int key, int value);
-/* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention */
+/* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention_varlen */
 void b200vit_debug_set_trace(void* dev_buf);
 
 #ifdef __cplusplus

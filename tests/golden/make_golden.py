@@ -24,6 +24,7 @@ sys.dont_write_bytecode = True
 from vit_pytorch import ViT, SimpleViT  # noqa: E402  (the reference)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
 
 CASES = {
     # BASELINE.json configs[0]: SimpleViT tiny (num_classes / mlp_dim chosen in SURVEY.md 8d)
@@ -120,7 +121,33 @@ def make_navit() -> None:
           f"{(packed - grouped).abs().max():.2e}; {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+from navit_c5_spec import NAVIT_C5, navit_config5_images, navit_config5_model  # noqa: E402  (tests/golden/)
+
+
+def make_navit_config5() -> None:
+    from vit_pytorch.na_vit import NaViT
+    model = navit_config5_model(NaViT)
+    imgs = navit_config5_images()
+    with torch.inference_mode():
+        fp32 = model([im.float() for im in imgs], group_images=True, group_max_seq_len=4096)
+        bf16 = model.bfloat16()([im for im in imgs], group_images=True, group_max_seq_len=4096)
+    d = (bf16.float() - fp32).abs()
+    floor = {"max": d.max().item(), "mean": d.mean().item(),
+             "frac_within_tol": (d <= 1e-3 + 1e-2 * fp32.abs()).float().mean().item()}
+    blob = {"name": "navit_config5", "kind": "navit", "spec": NAVIT_C5, "logits_fp32": fp32.clone(),
+            "logits_ref_bf16": bf16.clone(), "ref_bf16_floor": floor,
+            "versions": {"torch": str(torch.__version__), "reference": "vit-pytorch 1.23.6 @ /root/reference"}}
+    path = os.path.join(HERE, "navit_config5.pt")
+    torch.save(blob, path)
+    print(f"navit_config5: logits {tuple(fp32.shape)} |max| {fp32.abs().max():.4f}; reference-bf16 floor {floor}; "
+          f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "navit_config5":
+        make_navit_config5()
+        sys.exit(0)
     for n, s in CASES.items():
         make(n, s)
     make_navit()
+    make_navit_config5()

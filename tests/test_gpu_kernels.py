@@ -213,7 +213,11 @@ def test_gelu_epilogue_accuracy():
 
 
 @pytest.mark.parametrize("B,N,H", [(4, 197, 12), (3, 64, 3), (2, 257, 16), (5, 50, 4), (2, 16, 2), (2, 129, 2),
-                                   (1, 512, 1), (2, 1, 2)])
+                                   (1, 512, 1), (2, 1, 2),
+                                   # pipelined kernel (N <= 224): more units than SMs (several units per CTA, ring
+                                   # wrap-around of the 3 K/V stages), one-tile units, the 224-key TMEM limit, and 225
+                                   # keys = first shape of the round-1 kernel again
+                                   (40, 197, 12), (70, 196, 16), (200, 128, 3), (37, 224, 5), (3, 225, 2), (9, 33, 7)])
 def test_attention(B, N, H):
     torch.manual_seed(N)
     dh = 64
@@ -228,13 +232,13 @@ def test_attention(B, N, H):
     assert (out.float().cpu() - ref).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("knob,value", [(1, 1), (1, 2), (1, 3), (7, 8), (7, 16), (6, 1)])
-def test_attention_experimental_variants_stay_correct(knob, value):
-    """One-CTA-per-SM, 8-warps-per-tile, FMA-pipe exp2 and split-PV variants (b200vit_debug_set) are not the default
-    but must keep producing the same attention."""
+@pytest.mark.parametrize("knob,value,B,N", [(1, 1, 3, 197), (1, 1, 40, 128), (1, 1, 2, 50)])
+def test_attention_round1_kernels_agree_with_the_pipelined_one(knob, value, B, N):
+    """b200vit_debug_set(1, 1) routes N <= 224 to the round-1 kernels (the ones N > 224 always uses): both
+    implementations must produce the same attention."""
     L = _lib.lib()
     torch.manual_seed(7)
-    B, N, H, dh = 3, 197, 4, 64
+    H, dh = 4, 64
     qkv = torch.randn(B * N, 3 * H * dh, device=DEV).bfloat16()
     ref_out = torch.zeros(B * N, H * dh, device=DEV, dtype=torch.bfloat16)
     _lib.attention(qkv, ref_out, B, N, H, dh, dh ** -0.5)
@@ -245,7 +249,58 @@ def test_attention_experimental_variants_stay_correct(knob, value):
         torch.cuda.synchronize()
     finally:
         L.b200vit_debug_set(knob, 0)
-    assert within(out, ref_out.float(), rtol=2e-2, atol=2e-3) > 0.999
+    assert within(out, ref_out.float().cpu(), rtol=2e-2, atol=2e-3) > 0.999
+
+
+def test_attention_is_deterministic_and_batch_invariant():
+    """The persistent kernel strides units over CTAs: the same (image, head) must give the same bits wherever it
+    lands in the batch and on repeated launches."""
+    torch.manual_seed(11)
+    B, N, H, dh = 64, 197, 12, 64
+    qkv = torch.randn(B * N, 3 * H * dh, device=DEV).bfloat16()
+    out = torch.zeros(B * N, H * dh, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.zeros_like(out)
+    _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+    _lib.attention(qkv, out2, B, N, H, dh, dh ** -0.5)
+    assert torch.equal(out, out2)
+    sub = qkv[5 * N: 9 * N].contiguous()
+    out3 = torch.zeros(4 * N, H * dh, device=DEV, dtype=torch.bfloat16)
+    _lib.attention(sub, out3, 4, N, H, dh, dh ** -0.5)
+    assert torch.equal(out3, out[5 * N: 9 * N])
+
+
+def test_gemm_long_k_epilogue_warp_variants_agree():
+    """K >= 2048 fp32 epilogues run with 4 epilogue warps and one more operand stage (test hook 12 forces either)."""
+    torch.manual_seed(12)
+    M, N, K = 2048 + 64, 768, 3072
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.02).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    x0 = torch.randn(M, N, device=DEV)
+    res = {}
+    L = _lib.lib()
+    for ew in (4, 8):
+        L.b200vit_debug_set(12, ew)
+        try:
+            x = x0.clone()
+            xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+            st = torch.full((M, _lib.stats_parts(N), 2), float("nan"), device=DEV)
+            _lib.gemm(a, w, out_f32=x, out_bf16=xb, bias=bias, resid=x, stats_out=st)
+            y = torch.zeros(M, N, device=DEV)
+            _lib.gemm(a, w, out_f32=y, bias=bias)
+            torch.cuda.synchronize()
+        finally:
+            L.b200vit_debug_set(12, 0)
+        res[ew] = (x, xb, st.sum(dim=1), y)
+    ref = x0.cpu() + a.float().cpu() @ w.float().cpu().t() + bias.cpu()
+    for ew in (4, 8):
+        x, xb, st, y = res[ew]
+        assert torch.isfinite(st).all()
+        assert within(x, ref, rtol=1e-3, atol=2e-3) > 0.999
+        assert torch.equal(xb, x.bfloat16())
+        assert torch.allclose(st[:, 0].cpu(), xb.float().sum(1).cpu(), rtol=1e-3, atol=1e-2)
+        assert torch.allclose(st[:, 1].cpu(), (xb.float() ** 2).sum(1).cpu(), rtol=1e-3, atol=1e-2)
+    assert torch.equal(res[4][0], res[8][0]) and torch.equal(res[4][3], res[8][3])
 
 
 def test_attention_large_logits_are_stable():

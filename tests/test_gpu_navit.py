@@ -58,6 +58,34 @@ def test_navit_varied_resolutions_against_oracle():
     assert mx < 3e-2 and frac > 0.80
 
 
+def test_navit_config5_geometry_against_reference_golden():
+    """BASELINE.json configs[4] GEOMETRY: dim 1024, depth 6, heads 16, mlp 4096 (K = 1024 / N = 3072 head-norm QKV
+    epilogue, K = 4096 FC2), 10 images from 1 token to 32 x 32 patches = 1024 tokens.  Weights and images are rebuilt
+    from the seeds (tests/golden/navit_c5_spec.py); the expectation is the UNMODIFIED reference's fp32 forward and the
+    pass criterion its own bf16 error on the same inputs (both stored by make_golden.py in navit_config5.pt)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from navit_c5_spec import NAVIT_C5, navit_config5_images, navit_config5_model
+    g = load_golden("navit_config5")
+    assert g["spec"] == NAVIT_C5
+    m = navit_config5_model(NaViT).to(DEV, torch.bfloat16)
+    imgs = [im.to(DEV) for im in navit_config5_images()]
+    _lib.reset_launch_count()
+    with torch.inference_mode():
+        assert m.fused_reason(imgs) is None
+        out = m(imgs)
+        out_rows = m([imgs[:3], imgs[3:]])              # pre-packed rows: same images, same order
+    assert _lib.launch_count() > 0
+    ref, floor = g["logits_fp32"], g["ref_bf16_floor"]
+    mx, mean, frac = _stats(out, ref)
+    print(f"navit config-5 geometry fused vs reference fp32: max {mx:.5f} mean {mean:.5f} within {frac:.4f}; "
+          f"reference-bf16 floor max {floor['max']:.5f} mean {floor['mean']:.5f} within {floor['frac_within_tol']:.4f}")
+    assert out.shape == ref.shape and torch.isfinite(out.float()).all()
+    assert mx <= floor["max"] and mean <= floor["mean"] and frac >= floor["frac_within_tol"]
+    assert torch.equal(out, out_rows)
+
+
 @pytest.mark.parametrize("mode", [0, 1])      # 0: pipelined 64-key blocks (default); 1: serial 128-key blocks
 def test_varlen_attention_kernel_against_oracle(mode):
     lengths = [197, 1, 130, 577, 64, 1024, 129, 65, 63, 128, 300]

@@ -49,7 +49,8 @@ def test_module_state_dict_and_forward(g):
     assert torch.allclose(packed, g["logits_fp32"], rtol=1e-4, atol=2e-5)
     assert torch.allclose(grouped, g["logits_grouped_fp32"], rtol=1e-4, atol=2e-5)
     assert torch.allclose(single_row, g["logits_fp32"][:3], rtol=1e-4, atol=2e-5)
-    assert m.fused_reason() is not None                            # sm_100a path not built yet: stated, not hidden
+    assert m.fused_reason() is not None                            # no input given: stated, not hidden
+    assert m.fused_reason(imgs) == "input is not on a CUDA device"   # fp32 CPU call -> the PyTorch graph
 
 
 def test_patch_order_is_channel_major():
@@ -123,3 +124,24 @@ def test_navit_lnfold_prepared_tensors_reproduce_layernorm_linear():
         assert torch.allclose(got_qkv, want_qkv, rtol=2e-2, atol=2e-2), (got_qkv - want_qkv).abs().max()
         assert torch.allclose(got_h, want_h, rtol=2e-2, atol=2e-2), (got_h - want_h).abs().max()
         assert t[f"{i}.a.gqk"].numel() == 2 * 2 * 64 and t[f"{i}.a.qkvt"].abs().max() == 0
+
+
+def test_oracle_and_dropin_at_config5_geometry_equal_the_reference_golden():
+    """BASELINE.json configs[4] geometry (dim 1024, depth 6, heads 16, mlp 4096; images of 1 ... 1024 tokens): the
+    per-image oracle and the drop-in's own PyTorch graph, on weights rebuilt from the seeds, reproduce the fp32
+    logits the UNMODIFIED reference produced (tests/golden/navit_config5.pt, made by make_golden.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from navit_c5_spec import NAVIT_C5, navit_config5_images, navit_config5_model
+    g = load_golden("navit_config5")
+    assert g["spec"] == NAVIT_C5
+    m = navit_config5_model(NaViT)
+    imgs = [im.float() for im in navit_config5_images()]
+    ref = g["logits_fp32"]
+    got = NO.navit_forward(O.upcast(m.state_dict()), NAVIT_C5["kwargs"], [imgs])
+    assert got.shape == ref.shape == (len(imgs), 1000)
+    assert (got - ref).abs().max().item() < 2e-4, (got - ref).abs().max().item()
+    with torch.inference_mode():
+        own = m(imgs[:4] + imgs[8:])          # drop-in graph on a subset (the 1024- and 1-token images included)
+    assert (own - torch.cat([ref[:4], ref[8:]])).abs().max().item() < 2e-4

@@ -85,7 +85,7 @@ def lib() -> C.CDLL:
     L.b200vit_rmsnorm_heads.restype = i32
     L.b200vit_rmsnorm_heads.argtypes = [vp, i64, vp, i32, i32, i32, vp]
     L.b200vit_embed_varlen.restype = i32
-    L.b200vit_embed_varlen.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_embed_varlen.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
     L.b200vit_attn_pool.restype = i32
     L.b200vit_attn_pool.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.b200vit_mean_pool.restype = i32
@@ -107,6 +107,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the CURRENT device.  Every fused forward runs inside
+    `with torch.cuda.device(x.device)` (engine.on_device), so this is the stream of the tensors' device; the library
+    itself never calls cudaSetDevice."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -164,6 +167,9 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str) -> None:
         return
     if not t.is_cuda or t.dtype != dtype:
         raise B200VitError(f"{name}: expected CUDA {dtype}, got {t.device} {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        raise B200VitError(f"{name} lives on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "wrap the call in `with torch.cuda.device(tensor.device)`")
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None,
@@ -359,6 +365,7 @@ class VarlenIndex:
         self.dims = i32[3 * (S + 1):3 * (S + 1) + 2 * S]
         self.S, self.T, self.total_tiles, self.total_rows = S, cu[-1], tp[-1], rows[-1]
         self.max_w = max(dims[1::2])
+        self.max_gh, self.max_gw = max(dims[0::2]) // p, max(dims[1::2]) // p      # largest patch grid (pos tables)
         self.lengths = [cu[i + 1] - cu[i] for i in range(S)]
 
 
@@ -387,12 +394,15 @@ def embed_varlen(y: torch.Tensor, gamma: torch.Tensor, pos_h: torch.Tensor, pos_
     T, D = y.shape
     assert y.is_contiguous() and x.is_contiguous() and pos_h.is_contiguous() and pos_w.is_contiguous()
     assert T == index.T and x.shape == y.shape and pos_h.shape[1] == D and pos_w.shape[1] == D
+    if index.max_gh > pos_h.shape[0] or index.max_gw > pos_w.shape[0]:
+        raise IndexError(f"an image of {index.max_gh} x {index.max_gw} patches exceeds the positional tables "
+                         f"({pos_h.shape[0]} x {pos_w.shape[0]})")
     assert xb is None or (xb.is_contiguous() and xb.shape == y.shape)
     assert stats is None or (stats.is_contiguous() and stats.numel() == 2 * T)
     with _Timed("embed_varlen", bytes=y.numel() * 10):
-        rc = lib().b200vit_embed_varlen(_ptr(y), _ptr(gamma), _ptr(pos_h), _ptr(pos_w), _ptr(index.cu),
-                                        _ptr(index.dims), _ptr(x), _ptr(xb), _ptr(stats), T, D, index.S, p,
-                                        float(eps), _stream())
+        rc = lib().b200vit_embed_varlen(_ptr(y), _ptr(gamma), _ptr(pos_h), _ptr(pos_w), pos_h.shape[0],
+                                        pos_w.shape[0], _ptr(index.cu), _ptr(index.dims), _ptr(x), _ptr(xb),
+                                        _ptr(stats), T, D, index.S, p, float(eps), _stream())
     _check(rc, "b200vit_embed_varlen")
 
 

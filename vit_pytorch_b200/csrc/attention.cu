@@ -30,10 +30,6 @@ struct AttnParams {
   float scale_log2e;
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
-  int skip_max;           // experiment: skip the row-max pass (max := 0)
-  int exp_emul;           // 0 / 8 / 16 of every 32 exponentials on the FMA pipe instead of MUFU
-  long long* trace;       // timing experiment: [iteration][16] globaltimer stamps of CTA 0 (NULL = off)
-  int pv_split;           // accumulate O = P V in two independent TMEM tiles (even / odd key steps), summed on read
 };
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
@@ -41,16 +37,12 @@ __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { ret
 // TMEM_COLS = 512: one CTA per SM (NWG regions of 512/NWG columns).  TMEM_COLS = 256 (NWG = 1, one K/V/Q stage):
 // TWO independent CTAs per SM, each with one softmax warpgroup -- while one CTA waits for its MMAs or loads, the
 // other one's softmax keeps the MUFU / issue slots busy.
-// DBG = true compiles the experiment knobs of b200vit_debug_set (trace stamps, skip_max, pv_split, exp_emul) in; the
-// production instantiation (DBG = false) carries none of them.
-template <int NWG, int STAGES, int TMEM_COLS, bool DBG>
+// (The round-1 experiments -- FMA-pipe exp2, split PV accumulation, skipped row max, 8 warps per tile, globaltimer
+// traces -- are recorded in profiles/r01*; their code is gone.  Shapes with N <= 224 run attention_pipe.cu instead.)
+template <int NWG, int STAGES, int TMEM_COLS>
 __global__ void __launch_bounds__((4 * NWG + 2) * 32, TMEM_COLS == 256 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttnParams p) {
-  const int k_skip_max = DBG ? p.skip_max : 0;
-  const int k_exp_emul = DBG ? p.exp_emul : 0;
-  const int k_pv_split = DBG ? p.pv_split : 0;
-  long long* const k_trace = DBG ? p.trace : nullptr;
   constexpr int REGION = TMEM_COLS / NWG;
   constexpr int O_COL = REGION - ATT_DH;
   constexpr int NUM_SOFTMAX_WARPS = 4 * NWG;
@@ -127,9 +119,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);  // B = V is MN-major
-      auto stamp = [&](int it, int slot) {
-        if (k_trace && blockIdx.x == 0 && it < 64) k_trace[it * 16 + slot] = (long long)globaltimer_ns();
-      };
       // S_t(it) = Q_t K^T into region t  (waits until the epilogue of unit it-1 has drained the region)
       auto issue_s = [&](int it, int t) {
         const int s = it % STAGES;
@@ -147,7 +136,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         }
         umma_commit(&s_full[t]);
-        if (t == 0) stamp(it, 2);
       };
       // O_t(it) = P_t V  (A = P from TMEM, B = V as MN-major smem operand: 16 keys = two 8-row groups = 2048 B)
       auto issue_pv = [&](int it, int t) {
@@ -155,24 +143,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t sv = smem_u32(smem + s * stage_bytes) + kv_bytes;
         mbar_wait(&p_ready[t], it & 1);
         tc_fence_after();
-        if (t == 0) stamp(it, 3);
         const uint32_t d_o = tmem_base + t * REGION + O_COL;
         const int ksteps = p.KP / 16;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
-          // pv_split: two interleaved accumulation chains (the second tile sits 64 columns below the first)
-          const uint32_t d = (k_pv_split && (k & 1)) ? d_o - ATT_DH : d_o;
-          const uint32_t acc = k_pv_split ? (k >= 2) : (k != 0);
-          umma_ts(d, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, acc);
+          umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
         }
         umma_commit(&o_full[t]);
-        if (t == 0) stamp(it, 4);
       };
       auto wait_full = [&](int it) {
-        stamp(it, 0);
         mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);
         tc_fence_after();
-        stamp(it, 1);
       };
       const int n_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       if (NWG == 2 && STAGES == 2) {
@@ -220,11 +201,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // warps whose 32 query rows all lie beyond N skip the arithmetic but keep the barrier protocol in lockstep
       const bool warp_active = (round * NWG + t) * 128 + quad * 32 < p.N;
 
-      const bool tr = k_trace && blockIdx.x == 0 && warp == 0 && lane == 0 && it < 64;
-      if (tr) k_trace[it * 16 + 8] = (long long)globaltimer_ns();
       mbar_wait(&s_full[t], up);
       tc_fence_after();
-      if (tr) k_trace[it * 16 + 9] = (long long)globaltimer_ns();
       float sum = 1.f;
       if (warp_active) {
         // Columns [0, 32*nfull) need no key mask; the rest (< 48 columns) is handled 16 at a time with the mask.
@@ -240,11 +218,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     m3 = fmaxf(m3, __uint_as_float(R[j + 3]));                          \
   }
         int ci = 0;
-        if (k_skip_max) {
-          m0 = m1 = m2 = m3 = 0.f;
-          ci = 1 << 20;
-        }
-        if (!k_skip_max && nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
+        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
           tmem_ld_wait();
           tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
@@ -257,7 +231,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_wait();
           ATT_MAX32(ra)
         }
-        for (int c0 = nfull * 32; c0 < p.KP && !k_skip_max; c0 += 16) {
+        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
           uint32_t r16[16];
           tmem_ld_32x32b_x16(t_lane + c0, r16);
           tmem_ld_wait();
@@ -268,30 +242,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
         // ---------------- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-// E = number of leading elements of each 32-column chunk whose exponential is computed on the FMA pipe (exp2_emul2)
-#define ATT_EXP32_E(R, C0, E)                                                                 \
-  {                                                                                           \
-    uint32_t pk[16];                                                                          \
-    const f32x2 c2v = f2_make(c, c), nmc2v = f2_make(-mc, -mc);                               \
-    _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                       \
-      const f32x2 xa = f2_fma(f2_make(__uint_as_float(R[j]), __uint_as_float(R[j + 1])), c2v, nmc2v);     \
-      const f32x2 xb = f2_fma(f2_make(__uint_as_float(R[j + 2]), __uint_as_float(R[j + 3])), c2v, nmc2v); \
-      float e0, e1, e2, e3;                                                                   \
-      if (j < (E)) {                                                                          \
-        exp2_emul2(xa, e0, e1);                                                               \
-        exp2_emul2(xb, e2, e3);                                                               \
-      } else {                                                                                \
-        float x0, x1, x2, x3;                                                                 \
-        f2_get(xa, x0, x1);                                                                   \
-        f2_get(xb, x2, x3);                                                                   \
-        e0 = fast_ex2(x0); e1 = fast_ex2(x1); e2 = fast_ex2(x2); e3 = fast_ex2(x3);           \
-      }                                                                                       \
-      s0 += e0; s1 += e1; s2 += e2; s3 += e3;                                                 \
-      pk[j >> 1] = pack_bf16x2(e0, e1);                                                       \
-      pk[(j >> 1) + 1] = pack_bf16x2(e2, e3);                                                 \
-    }                                                                                         \
-    tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
-  }
 #define ATT_EXP32_PLAIN(R, C0)                                                                \
   {                                                                                           \
     uint32_t pk[16];                                                                          \
@@ -306,10 +256,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }                                                                                         \
     tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                             \
   }
-#define ATT_EXP32(R, C0)                                            \
-  if (DBG && k_exp_emul == 8) ATT_EXP32_E(R, C0, 8)                 \
-  else if (DBG && k_exp_emul == 16) ATT_EXP32_E(R, C0, 16)          \
-  else ATT_EXP32_PLAIN(R, C0)
+#define ATT_EXP32(R, C0) ATT_EXP32_PLAIN(R, C0)
         ci = 0;
         if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
         for (; ci + 1 < nfull; ci += 2) {
@@ -341,7 +288,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
 #undef ATT_MAX32
 #undef ATT_EXP32
-#undef ATT_EXP32_E
 #undef ATT_EXP32_PLAIN
         sum = (s0 + s1) + (s2 + s3);
         tmem_st_wait();
@@ -349,31 +295,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[t]);
-      if (tr) k_trace[it * 16 + 10] = (long long)globaltimer_ns();
 
       // epilogue: O / sum -> bf16 -> global
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
-      if (tr) k_trace[it * 16 + 11] = (long long)globaltimer_ns();
       uint32_t ob[32];  // 64 output columns as packed bf16 pairs
       if (warp_active) {
-        uint32_t r0[32], r1[32];
-        const bool split = k_pv_split && p.KP >= 32;
+        uint32_t r0[32];
 #pragma unroll
         for (int hcol = 0; hcol < 2; ++hcol) {
           tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
-          if (split) tmem_ld_32x32b_x32(t_lane + O_COL - ATT_DH + 32 * hcol, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(r0[2 * j]), bb = __uint_as_float(r0[2 * j + 1]);
-            if (split) {
-              a += __uint_as_float(r1[2 * j]);
-              bb += __uint_as_float(r1[2 * j + 1]);
-            }
-            ob[16 * hcol + j] = pack_bf16x2(a * inv, bb * inv);
-          }
+          for (int j = 0; j < 16; ++j)
+            ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
         }
       }
       tc_fence_before();
@@ -384,7 +320,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
-      if (tr) k_trace[it * 16 + 12] = (long long)globaltimer_ns();
     }
   }
 
@@ -396,27 +331,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-// debug / experiment knobs (b200vit_debug_set)
-static int g_attn_mode = 0;      // 0 auto, 1 force the one-CTA-per-SM variants, 2 / 3 the 8-warps-per-tile variants
-int launch_attention_split_variant(int variant, const void* qkv, void* out, int B, int N, int H, float scale,
-                                   cudaStream_t stream);
-static int g_attn_skip_max = 0;  // experiment only
-static int g_attn_pv_split = 0;
-static int g_attn_exp_emul = 0;
-static long long* g_attn_trace = nullptr;
-static int g_attn_v_lbo = 1024;  // V descriptor leading-dim byte offset
-static int g_attn_v_sbo = 1024;  // V descriptor stride-dim byte offset
+// test hooks (b200vit_debug_set): process-global, NOT part of the re-entrant API
+static std::atomic<int> g_attn_mode{0};   // 0 auto (pipelined kernel when N <= 224), 1 force the round-1 kernels below
+static std::atomic<int> g_attn_v_lbo{1024};  // V descriptor leading-dim byte offset (bring-up probe)
+static std::atomic<int> g_attn_v_sbo{1024};  // V descriptor stride-dim byte offset
+
+bool attention_pipe_eligible(int N, int dh);
+int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
+                          cudaStream_t stream);
 
 template <int NWG, int STAGES, int TMEM_COLS = 512>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, size_t smem_bytes,
                             cudaStream_t stream) {
-  const bool dbg = p.trace || p.skip_max || p.exp_emul || p.pv_split;
-  auto kern = dbg ? attention_kernel<NWG, STAGES, TMEM_COLS, true> : attention_kernel<NWG, STAGES, TMEM_COLS, false>;
-  static size_t smem_set[2] = {0, 0};
-  if (smem_bytes > smem_set[dbg]) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    smem_set[dbg] = smem_bytes;
-  }
+  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS>;
+  B200_ENSURE_SMEM(kern, smem_bytes);
   const int slots = num_sms() * (TMEM_COLS == 256 ? 2 : 1);
   const int grid = p.units < slots ? p.units : slots;
   kern<<<grid, (4 * NWG + 2) * 32, smem_bytes, stream>>>(tmQ, tmKV, p);
@@ -430,7 +358,6 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, con
 using namespace b200;
 
 extern "C" void b200vit_debug_set_trace(void* dev_buf) {
-  g_attn_trace = reinterpret_cast<long long*>(dev_buf);
   attention_varlen_set_trace(reinterpret_cast<long long*>(dev_buf));
 }
 
@@ -440,12 +367,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 2: g_attn_v_lbo = value; return 0;
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
-    case 5: g_attn_skip_max = value; return 0;
-    case 6: g_attn_pv_split = value; return 0;
-    case 7: g_attn_exp_emul = value; return 0;
-    case 8: gemm2_set_feed_skip(value); return 0;
-    case 9: gemm2_set_l2_prefetch(value); return 0;
-    case 10: gemm2_set_stage_limit(value); return 0;
+    case 12: gemm2_force_epilogue_warps(value); return 0;
     case 11: attention_varlen_set_mode(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
@@ -458,14 +380,16 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   B200_CHECK_ARG(N <= 512, "attention: N=%d > 512 needs the (unbuilt) online-softmax path", N);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "attention: pointers must be 16-byte aligned");
-  if ((g_attn_mode == 2 || g_attn_mode == 3) && N > 128 && N <= 256)
-    return launch_attention_split_variant(g_attn_mode, qkv, out, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
+  const int mode = g_attn_mode.load();
+  if (mode != 1 && attention_pipe_eligible(N, dh))
+    return launch_attention_pipe(qkv, out, B, N, H, scale, (unsigned)g_attn_v_lbo.load(), (unsigned)g_attn_v_sbo.load(),
+                                 reinterpret_cast<cudaStream_t>(stream));
   AttnParams p{};
   p.B = B; p.N = N; p.H = H;
   p.I = H * dh;
   p.KP = (N + 15) / 16 * 16;
   // occupancy 2 (two single-warpgroup CTAs per SM, 256 TMEM columns each) whenever one region can hold S | P | O
-  const bool occ2 = g_attn_mode != 1 && p.KP <= 256;
+  const bool occ2 = p.KP <= 256;
   const int nwg = occ2 ? 1 : ((N > 128 && p.KP <= 256) ? 2 : 1);
   p.kv_boxes = (p.KP + 255) / 256;
   p.kv_box_rows = ((p.KP + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
@@ -474,13 +398,8 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.units = B * H * p.rounds;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.trace = g_attn_trace;
-  p.skip_max = g_attn_skip_max;
-  p.exp_emul = g_attn_exp_emul;
-  // the second O tile occupies [O_COL-64, O_COL): it must not overlap P at [0, KP/2)
-  p.pv_split = (g_attn_pv_split && p.KP / 2 <= (occ2 || (N > 128 && p.KP <= 256) ? 256 : 512) - 2 * ATT_DH) ? 1 : 0;
-  p.v_lbo = (unsigned)g_attn_v_lbo;
-  p.v_sbo = (unsigned)g_attn_v_sbo;
+  p.v_lbo = (unsigned)g_attn_v_lbo.load();
+  p.v_sbo = (unsigned)g_attn_v_sbo.load();
 
   CUtensorMap tmQ, tmKV;
   const uint64_t dims[3] = {(uint64_t)3 * p.I, (uint64_t)N, (uint64_t)B};

@@ -660,14 +660,8 @@ extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_
     if (rc) return rc;
     rc = encode_tmap_bf16(&tmKV, qkv, 2, dims, strides, kvbox);
     if (rc) return rc;
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel<false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, av2::DYN_BYTES));
-      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen2_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, av2::DYN_BYTES));
-      attr2_set = true;
-    }
+    B200_ENSURE_SMEM(attention_varlen2_kernel<false>, av2::DYN_BYTES);
+    B200_ENSURE_SMEM(attention_varlen2_kernel<true>, av2::DYN_BYTES);
     p.trace = g_varlen_trace;
     if (p.trace) attention_varlen2_kernel<true><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
     else attention_varlen2_kernel<false><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
@@ -676,12 +670,7 @@ extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_
     const uint32_t box[2] = {64, 128};
     int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-      B200_CHECK_CUDA(cudaFuncSetAttribute(attention_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           DYN_BYTES));
-      attr_set = true;
-    }
+    B200_ENSURE_SMEM(attention_varlen_kernel, DYN_BYTES);
     attention_varlen_kernel<<<grid, THREADS, DYN_BYTES, st>>>(tm, p);
   }
   B200_CHECK_CUDA(cudaGetLastError());

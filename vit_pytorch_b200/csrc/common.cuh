@@ -31,6 +31,16 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  A kernel launched with the programmaticStreamSerialization attribute may
+// start while its predecessor in the stream is still running: pdl_wait() blocks until the predecessor has COMPLETED
+// and its memory is visible (no-op without the attribute); nothing before it may read the predecessor's results or
+// write anything the predecessor reads.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as
+// SM resources free up (they sit in their own pdl_wait until this whole grid has finished).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

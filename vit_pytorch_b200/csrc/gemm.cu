@@ -309,11 +309,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using L = GemmSmem<BLOCK_N, STAGES>;
   auto kern = gemm_bf16_kernel<BLOCK_N, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
-  }
+  B200_ENSURE_SMEM(kern, L::DYN_BYTES);
   p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;

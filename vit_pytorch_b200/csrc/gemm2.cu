@@ -33,10 +33,12 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_BUF_BYTES = 4096;                   // one 32-row x 128-byte swizzled box
-template <int MODE>
+// EW = epilogue warps per CTA.  MODE_BF16: 16.  fp32 modes: 8, or 4 for long-K problems (FC2: the 48 k-blocks of a
+// tile leave the epilogue ample time, and halving its staging boxes buys a fifth operand stage).
+template <int MODE, int EW>
 struct Cfg {
-  static constexpr int STAGES = MODE == MODE_DUAL ? 4 : 5;
-  static constexpr int EPI_WARPS = MODE == MODE_BF16 ? 16 : 8;
+  static constexpr int EPI_WARPS = EW;
+  static constexpr int STAGES = MODE == MODE_DUAL ? (EW == 4 ? 5 : 4) : (MODE == MODE_F32 && EW == 4 ? 6 : 5);
   static constexpr int BUFS_PER_WARP = MODE == MODE_BF16 ? 1 : (MODE == MODE_DUAL ? 3 : 2);
   static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
@@ -61,9 +63,6 @@ struct Gemm2Params {
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
   const float* head_gamma;  // EPI_HEADNORM: fp32 [norm_cols] scale of the RMS-normalised leading heads
   int norm_cols;            //               columns [0, norm_cols) are normalised per 64-wide head
-  int l2_prefetch;   // A tiles are prefetched into L2 this many k blocks ahead of the shared-memory pipeline (0: off)
-  int stage_limit;   // experiment (debug key 10): use only this many of the operand ring's stages (0: all)
-  int feed_skip;     // experiment (debug key 8): load the B tile only every (feed_skip+1)-th k block (WRONG results)
 };
 
 // LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32), on fp32 PAIRS (FFMA2):
@@ -130,13 +129,13 @@ __device__ __forceinline__ void prefetch_cols(const Gemm2Params& p, int flags, i
 }
 
 // CTF: the epilogue flags as a compile-time constant (the inner loops then carry no flag tests), or -1 = read p.flags
-template <int MODE, int CTF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::Cfg<MODE>::NUM_THREADS, 1)
+template <int MODE, int CTF, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::Cfg<MODE, EW>::NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmResid,
              const __grid_constant__ CUtensorMap tmOutB, const Gemm2Params p) {
   using namespace g2;
-  using C = Cfg<MODE>;
+  using C = Cfg<MODE, EW>;
   constexpr int STAGES = C::STAGES;
   constexpr int EPI_WARPS = C::EPI_WARPS;
   constexpr int COLS_PER_WARP = C::COLS_PER_WARP;
@@ -166,7 +165,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], p.feed_skip >= 2000 ? 2 : 1);  // (no-load experiment: the peer arrives explicitly)
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -190,8 +189,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+  // the tail of the previous kernel in the stream; from here on its results are read and ours are written.
+  pdl_wait();
+  pdl_launch_dependents();
+
   const int num_tiles = p.num_m_pairs * p.num_n_tiles;
-  const int nst = (p.stage_limit > 0 && p.stage_limit < STAGES) ? p.stage_limit : STAGES;  // (pipeline-depth probe)
+  constexpr int nst = STAGES;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -205,38 +209,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_blk = tile % p.num_n_tiles;
         const int m0 = m_pair * (2 * BLOCK_M) + rank * BLOCK_M;
         const int n0 = n_blk * BLOCK_N + rank * (BLOCK_N / 2);
-        if (p.l2_prefetch > 0 && tile == cluster_id) {  // first tile: warm the head of its A panel
-          for (int kb = 0; kb < p.l2_prefetch && kb < p.num_k_blocks; ++kb) tma_prefetch_l2_2d(&tmA, kb * BLOCK_K, m0);
-        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          if (p.l2_prefetch > 0) {
-            // the A panel streams from HBM (it is the previous kernel's output and larger than L2): request it
-            // l2_prefetch k blocks ahead, across the tile boundary, so the smem ring only has to cover L2 latency
-            const int kp = kb + p.l2_prefetch;
-            if (kp < p.num_k_blocks) {
-              tma_prefetch_l2_2d(&tmA, kp * BLOCK_K, m0);
-            } else if (tile + num_clusters < num_tiles && kp - p.num_k_blocks < p.num_k_blocks) {
-              const int m_next = ((tile + num_clusters) / p.num_n_tiles) * (2 * BLOCK_M) + rank * BLOCK_M;
-              tma_prefetch_l2_2d(&tmA, (kp - p.num_k_blocks) * BLOCK_K, m_next);
-            }
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          // feed_skip: 1..1999 B only every (s+1)-th k block; 2000..3999 neither A nor B after the first k block;
-          // >= 4000 A only on the first k block, B always
-          const bool load_b = p.feed_skip == 0 || p.feed_skip >= 4000 || (kb % (p.feed_skip + 1)) == 0;
-          const bool load_a = p.feed_skip < 2000 || kb == 0;
-          const uint32_t bytes = (load_a ? 2 * A_BYTES : 0) + (load_b ? 2 * (STAGE_BYTES - A_BYTES) : 0);
-          if (leader) {
-            if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            else mbar_arrive(&full_bar[stage]);
-          } else if (p.feed_skip >= 2000) {
-            mbar_arrive_cluster(full_leader);  // keeps the peer's producer in lock step when nothing is loaded
-          }
-          if (load_a) tma_load_2d_cg2(sa, &tmA, full_leader, kb * BLOCK_K, m0);
-          if (load_b) tma_load_2d_cg2(sb, &tmB, full_leader, kb * BLOCK_K, n0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          tma_load_2d_cg2(sa, &tmA, full_leader, kb * BLOCK_K, m0);
+          tma_load_2d_cg2(sb, &tmB, full_leader, kb * BLOCK_K, n0);
           if (++stage == nst) {
             stage = 0;
             phase ^= 1;
@@ -534,9 +514,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ++box_seq;
         }
         if (DUAL && row_ok) {
+          // one statistics slot per 128 output columns: with 8 warps each column half of the tile has its own warp,
+          // with 4 warps this warp covered both halves (the second slot is written as zero)
           const int part = n_blk * 2 + (e >> 2);
-          *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part)) =
-              make_float2(st_sum, st_sq);
+          float2* sp = reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part));
+          sp[0] = make_float2(st_sum, st_sq);
+          if (EPI_WARPS == 4 && part + 1 < p.stats_parts) sp[1] = make_float2(0.f, 0.f);
         }
         if (++acc == 2) {
           acc = 0;
@@ -556,19 +539,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-static int g_gemm_l2_prefetch = 0;
-void gemm2_set_l2_prefetch(int v) { g_gemm_l2_prefetch = v; }
-static int g_gemm_stage_limit = 0;
-void gemm2_set_stage_limit(int v) { g_gemm_stage_limit = v; }
-static int g_gemm_feed_skip = 0;  // experiment knob, see Gemm2Params::feed_skip
-void gemm2_set_feed_skip(int v) { g_gemm_feed_skip = v; }
-static int g_gemm_force = 0;  // debug: 0 auto, 1 force v1, 2 force v2 (wherever its epilogue applies)
+static std::atomic<int> g_gemm_force{0};  // test hook: 0 auto, 1 force v1, 2 force v2 (wherever its epilogue applies)
+static std::atomic<int> g_gemm_ew{0};     // test hook: 0 auto, 4 / 8 force the epilogue-warp count of the fp32 modes
 
 int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_bf16, const float* out_f32,
                    const float* resid) {
   (void)K;
   (void)resid;
-  if (g_gemm_force == 1) return 0;
+  if (g_gemm_force.load() == 1) return 0;
   const bool dual = out_bf16 && out_f32;
   if (dual) {
     // fp32 stream (in place, residual) + bf16 copy + statistics: the LN-fold producer epilogue
@@ -582,23 +560,20 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
   if (out_bf16 && (ldo % 8) != 0) return 0;  // TMA: 16-byte row pitch
   if (out_f32 && (ldo % 4) != 0) return 0;
   if ((N % 4) != 0) return 0;                // float4 bias / col_s loads
-  if (g_gemm_force == 2) return 1;
+  if (g_gemm_force.load() == 2) return 1;
   return (M >= 1024 && N >= 256) ? 1 : 0;    // small problems: the single-CTA kernel has finer tiles
 }
 
-template <int MODE, int CTF>
+template <int MODE, int CTF, int EW>
 static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmResid, const CUtensorMap& tmOutB, const Gemm2Params& p, int clusters,
                           cudaStream_t stream) {
-  using C = g2::Cfg<MODE>;
-  auto kern = gemm2_kernel<MODE, CTF>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::DYN_BYTES));
-    attr_set = true;
-  }
-  kern<<<2 * clusters, C::NUM_THREADS, C::DYN_BYTES, stream>>>(tmA, tmB, tmOut, tmResid, tmOutB, p);
-  B200_CHECK_CUDA(cudaGetLastError());
+  using C = g2::Cfg<MODE, EW>;
+  static_assert(C::DYN_BYTES <= 227 * 1024, "gemm2: shared memory budget");
+  auto kern = gemm2_kernel<MODE, CTF, EW>;
+  B200_ENSURE_SMEM(kern, C::DYN_BYTES);
+  B200_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(C::NUM_THREADS), C::DYN_BYTES, stream, /*pdl=*/true,
+                                tmA, tmB, tmOut, tmResid, tmOutB, p));
   count_launch();
   return 0;
 }
@@ -625,9 +600,6 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.col_s = col_s;
   p.head_gamma = head_gamma;
   p.norm_cols = norm_cols;
-  p.feed_skip = g_gemm_feed_skip;
-  p.l2_prefetch = g_gemm_l2_prefetch;
-  p.stage_limit = g_gemm_stage_limit;
 
   CUtensorMap tmA, tmB, tmOut, tmResid, tmOutB;
   {
@@ -670,16 +642,24 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-#define B200_G2_LAUNCH(MODE, CTF) launch_gemm2_t<MODE, CTF>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream)
+#define B200_G2_LAUNCH_EW(MODE, CTF, EW) \
+  launch_gemm2_t<MODE, CTF, EW>(tmA, tmB, tmOut, tmResid, tmOutB, p, clusters, stream)
+#define B200_G2_LAUNCH(MODE, CTF) B200_G2_LAUNCH_EW(MODE, CTF, (MODE == MODE_BF16 ? 16 : 8))
+  // long-K fp32 epilogues (FC2): 4 epilogue warps, one more operand stage
+  const int ew_force = g_gemm_ew.load();
+  const bool ew4 = ew_force == 4 || (ew_force == 0 && K >= 2048);
   constexpr int F_BIAS = B200VIT_EPI_BIAS, F_GELU = B200VIT_EPI_GELU, F_RES = B200VIT_EPI_RESIDUAL,
                 F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS, F_HN = B200VIT_EPI_HEADNORM;
   // the flag combinations of a transformer block get their own instantiation, anything else the generic kernel
   if (dual) {
-    if (flags == (F_BIAS | F_RES | F_STATS)) return B200_G2_LAUNCH(MODE_DUAL, F_BIAS | F_RES | F_STATS);
-    if (flags == (F_RES | F_STATS)) return B200_G2_LAUNCH(MODE_DUAL, F_RES | F_STATS);
+    if (flags == (F_BIAS | F_RES | F_STATS))
+      return ew4 ? B200_G2_LAUNCH_EW(MODE_DUAL, F_BIAS | F_RES | F_STATS, 4)
+                 : B200_G2_LAUNCH(MODE_DUAL, F_BIAS | F_RES | F_STATS);
+    if (flags == (F_RES | F_STATS))
+      return ew4 ? B200_G2_LAUNCH_EW(MODE_DUAL, F_RES | F_STATS, 4) : B200_G2_LAUNCH(MODE_DUAL, F_RES | F_STATS);
     return B200_G2_LAUNCH(MODE_DUAL, -1);
   }
-  if (out_f32) return B200_G2_LAUNCH(MODE_F32, -1);
+  if (out_f32) return ew4 ? B200_G2_LAUNCH_EW(MODE_F32, -1, 4) : B200_G2_LAUNCH(MODE_F32, -1);
   if (flags & F_HN) {  // (only reached through b200vit_gemm_headnorm_bf16)
     if (flags == (F_HN | F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_HN | F_FOLD | F_BIAS);
     if (flags == F_HN) return B200_G2_LAUNCH(MODE_BF16, F_HN);
@@ -690,8 +670,10 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   if (flags == (F_BIAS | F_GELU)) return B200_G2_LAUNCH(MODE_BF16, F_BIAS | F_GELU);
   return B200_G2_LAUNCH(MODE_BF16, -1);
 #undef B200_G2_LAUNCH
+#undef B200_G2_LAUNCH_EW
 }
 
 void gemm_force_version(int v) { g_gemm_force = v; }
+void gemm2_force_epilogue_warps(int v) { g_gemm_ew = v; }
 
 }  // namespace b200

@@ -446,15 +446,8 @@ extern "C" int b200vit_patchify_ln(const void* img, const float* gamma, const fl
   const int wp = (W + 31) / 32 * 32 + 16;  // fast path: padded slab row (stride = 16 bytes mod 64: no bank conflicts)
   const size_t smem = fast ? (size_t)C * 16 * wp * 2 + 2 * 768 * sizeof(float) : (size_t)C * ph * W * 2;
   B200_CHECK_ARG(smem <= 200 * 1024, "patchify_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
-  static size_t smem_set[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > smem_set[fast]) {
-    if (fast)
-      B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln16c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-    else
-      B200_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[fast] = smem;
-  }
+  if (fast) B200_ENSURE_SMEM(patchify_ln16c3_kernel, smem);
+  else B200_ENSURE_SMEM(patchify_ln_kernel, smem);
   const int nrows = B * (H / ph);
   const int per_sm = (int)(200 * 1024 / (smem + 1024)) < 8 ? (int)(200 * 1024 / (smem + 1024)) : 8;
   int grid = num_sms() * (per_sm < 1 ? 1 : per_sm);
@@ -638,7 +631,7 @@ __global__ void __launch_bounds__(256)
 embed_varlen_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ pos_h,
                     const float* __restrict__ pos_w, const int* __restrict__ cu, const int* __restrict__ dims,
                     float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int T, int D,
-                    int S, int p, float eps) {
+                    int S, int p, float eps, int pos_h_rows, int pos_w_rows) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -648,9 +641,11 @@ embed_varlen_kernel(const float* __restrict__ y, const float* __restrict__ gamma
     if (cu[mid] <= row) lo = mid; else hi = mid;
   }
   const int local = (int)row - cu[lo];
-  const int gw = dims[2 * lo + 1] / p;
-  const float* ph = pos_h + (long long)(local / gw) * D;
-  const float* pw = pos_w + (long long)(local % gw) * D;
+  // the host binding rejects grids larger than the tables (the reference raises an index error there); the clamps
+  // only make sure a foreign caller of the C ABI can never read outside them
+  const int gw = max(dims[2 * lo + 1] / p, 1);
+  const float* ph = pos_h + (long long)min(local / gw, pos_h_rows - 1) * D;
+  const float* pw = pos_w + (long long)min(local % gw, pos_w_rows - 1) * D;
   const float* yr = y + row * D;
   float* xr = x + row * D;
   __nv_bfloat16* xbr = xb ? xb + row * D : nullptr;
@@ -711,13 +706,15 @@ extern "C" int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H
 }
 
 extern "C" int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h, const float* pos_w,
-                                    const int32_t* cu_seqlens_dev, const int32_t* dims_dev, float* x, void* xb_bf16,
-                                    float* stats, int T, int D, int S, int p, float eps, void* stream) {
+                                    int pos_h_rows, int pos_w_rows, const int32_t* cu_seqlens_dev,
+                                    const int32_t* dims_dev, float* x, void* xb_bf16, float* stats, int T, int D, int S,
+                                    int p, float eps, void* stream) {
   B200_CHECK_ARG(y && gamma && pos_h && pos_w && cu_seqlens_dev && dims_dev && x, "embed_varlen: null pointer");
+  B200_CHECK_ARG(pos_h_rows > 0 && pos_w_rows > 0, "embed_varlen: empty positional table");
   B200_CHECK_ARG(T > 0 && S > 0 && p > 0 && D > 0 && (D % 4) == 0, "embed_varlen: bad shape T=%d D=%d S=%d", T, D, S);
   b200::embed_varlen_kernel<<<(T + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       y, gamma, pos_h, pos_w, cu_seqlens_dev, dims_dev, x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, T, D, S, p,
-      eps);
+      eps, pos_h_rows, pos_w_rows);
   B200_CHECK_CUDA(cudaGetLastError());
   b200::count_launch();
   return 0;
@@ -902,16 +899,8 @@ extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int
   const int wp = (max_w + 31) / 32 * 32 + 16;  // fast path: slab row stride in pixels (= 16 bytes mod 64: no bank conflicts)
   const size_t smem = fast ? (size_t)C * 16 * wp * 2 : (size_t)C * p * max_w * 2;
   B200_CHECK_ARG(smem <= 200 * 1024, "patchify_varlen_ln: patch-row slab of %zu bytes exceeds shared memory", smem);
-  static size_t smem_set[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > smem_set[fast]) {
-    if (fast)
-      B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln16_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      B200_CHECK_CUDA(cudaFuncSetAttribute(b200::patchify_varlen_ln_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[fast] = smem;
-  }
+  if (fast) B200_ENSURE_SMEM(b200::patchify_varlen_ln16_kernel, smem);
+  else B200_ENSURE_SMEM(b200::patchify_varlen_ln_kernel, smem);
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;

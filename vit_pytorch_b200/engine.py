@@ -39,6 +39,20 @@ def ln_mode() -> str:
     return m
 
 
+def on_device(t: torch.Tensor):
+    """Context manager that makes t's GPU the current device for the duration of a fused forward: the library
+    enqueues on torch's current stream of the CURRENT device and keeps its per-device state by cudaGetDevice, so a
+    model on cuda:1 must not be launched while cuda:0 is current."""
+    return torch.cuda.device(t.device)
+
+
+def _global_hooks() -> bool:
+    """Hooks installed with torch.nn.modules.module.register_module_forward_hook & co. observe every submodule call,
+    so they need the PyTorch graph exactly like per-module hooks do."""
+    mod = torch.nn.modules.module
+    return bool(getattr(mod, "_global_forward_hooks", None)) or bool(getattr(mod, "_global_forward_pre_hooks", None))
+
+
 def _has_hooks(m: nn.Module) -> bool:
     return bool(m._forward_hooks) or bool(m._forward_pre_hooks) or bool(getattr(m, "_backward_hooks", None))
 
@@ -46,6 +60,8 @@ def _has_hooks(m: nn.Module) -> bool:
 def hooks_inside(root: nn.Module, skip: Tuple[nn.Module, ...] = ()) -> bool:
     """True if any submodule strictly inside `root` carries a forward(-pre) hook (Recorder / Extractor style
     introspection, reference recorder.py:25-30): those need the materialised eager graph."""
+    if _global_hooks():
+        return True
     for m in root.modules():
         if m is root or any(m is s for s in skip):
             continue
@@ -67,7 +83,9 @@ def why_not_fused(params: List[torch.Tensor], x: torch.Tensor, *, training: bool
             return "parameters and input on different devices"
         if p.dtype != torch.bfloat16:
             return f"parameter dtype {p.dtype} (fused path is bf16)"
-    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        # also a frozen model fed by something trainable (prompts, an upstream module, saliency w.r.t. the input):
+        # the fused kernels are forward only and would silently cut the graph
         return "autograd is recording (fused path is forward only)"
     if training and dropout_p > 0.0:
         return "dropout is active"
@@ -84,8 +102,37 @@ class _Prepared:
         self.t: Dict[str, torch.Tensor] = {}
 
 
+# bumped by refresh_fused_weights(): part of every prepared-weight key, so one call invalidates every engine of the
+# process.  (p._version catches in-place ops on the parameter; writes through `p.data` -- EMA updates, manual
+# weight loading -- do NOT bump it, hence the explicit epoch; load_state_dict / .to() / .half() of the drop-in
+# modules call refresh_fused_weights() themselves.)
+_WEIGHT_EPOCH = [0]
+
+
+def refresh_fused_weights() -> None:
+    """Drop every cached bf16 / LN-folded copy of the parameters; the next fused forward rebuilds them."""
+    _WEIGHT_EPOCH[0] += 1
+
+
 def _version_key(params: List[torch.Tensor]) -> tuple:
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return (_WEIGHT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
+
+
+class FusedWeightsMixin:
+    """nn.Module mixin: state-changing entry points that bypass parameter versions invalidate the fused copies."""
+
+    def refresh_fused_weights(self) -> None:
+        refresh_fused_weights()
+
+    def load_state_dict(self, *args, **kwargs):            # copy_ under no_grad bumps _version, but be explicit
+        out = super().load_state_dict(*args, **kwargs)
+        refresh_fused_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):                 # .to() / .cuda() / .bfloat16(): new storages
+        out = super()._apply(fn, *args, **kwargs)
+        refresh_fused_weights()
+        return out
 
 
 def _f32(p: torch.Tensor) -> torch.Tensor:
@@ -168,7 +215,8 @@ class TransformerEngine:
     def workspace(self, M: int, device: torch.device) -> Dict[str, torch.Tensor]:
         attn0, ff0 = next(iter(self._layers()))
         D, I, Hd = attn0.dim, attn0.heads * attn0.dim_head, ff0.hidden_dim
-        key = (M, D, I, Hd, device)
+        # one workspace per (shape, stream): two streams running the same model must not share scratch buffers
+        key = (M, D, I, Hd, device, torch.cuda.current_stream(device).cuda_stream)
         if self.ws_key != key:
             bf = dict(device=device, dtype=torch.bfloat16)
             self.ws = {
@@ -211,37 +259,39 @@ class TransformerEngine:
                 _lib.rowstats_cast(x, xb, ws["stats_in"])
             for i, (attn, ff) in enumerate(self._layers()):
                 _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
-                          ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"])
+                          ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"], ln_eps=attn.norm.eps)
                 self._attention(ws, B, N, attn)
                 _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
                           stats_out=sb)
                 _lib.gemm(xb, t[f"{i}.fc1.wg"], out_bf16=ws["h"], bias=t[f"{i}.fc1.t"], gelu=True, ln_sums=sb,
-                          col_s=t[f"{i}.fc1.s"])
+                          col_s=t[f"{i}.fc1.s"], ln_eps=ff.parts()[0].eps)
                 _lib.gemm(ws["h"], t[f"{i}.fc2.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.fc2.b"], resid=x,
                           stats_out=sa)
             return
         for i, (attn, ff) in enumerate(self._layers()):
-            _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"])
+            _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"], eps=attn.norm.eps)
             _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
             self._attention(ws, B, N, attn)
             _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, bias=t[f"{i}.out.b"], resid=x)
-            _lib.layernorm(x, t[f"{i}.ln2.w"], t[f"{i}.ln2.b"], out_bf16=ws["xn"])
+            _lib.layernorm(x, t[f"{i}.ln2.w"], t[f"{i}.ln2.b"], out_bf16=ws["xn"], eps=ff.parts()[0].eps)
             _lib.gemm(ws["xn"], t[f"{i}.fc1.w"], out_bf16=ws["h"], bias=t[f"{i}.fc1.b"], gelu=True)
             _lib.gemm(ws["h"], t[f"{i}.fc2.w"], out_f32=x, bias=t[f"{i}.fc2.b"], resid=x)
 
     def final_norm(self, x: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None,
                    out_f32: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None) -> None:
         t = self.prepared()
-        _lib.layernorm(x, t["norm.w"], t["norm.b"], out_bf16=out_bf16, out_f32=out_f32, row_index=row_index)
+        _lib.layernorm(x, t["norm.w"], t["norm.b"], out_bf16=out_bf16, out_f32=out_f32, row_index=row_index,
+                       eps=self.mod.norm.eps)
 
     def forward_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
         """Transformer.forward on arbitrary bf16 tokens [B, N, D] (what MAE / SimMIM / Distill call,
         reference mae.py:74, simmim.py:70, distill.py:66)."""
         B, N, D = tokens.shape
-        x = tokens.reshape(B * N, D).float().contiguous()
-        self.run_blocks(x, B, N)
-        out = torch.empty(B * N, D, device=tokens.device, dtype=torch.bfloat16)
-        self.final_norm(x, out_bf16=out)
+        with on_device(tokens):
+            x = tokens.reshape(B * N, D).float().contiguous()
+            self.run_blocks(x, B, N)
+            out = torch.empty(B * N, D, device=tokens.device, dtype=torch.bfloat16)
+            self.final_norm(x, out_bf16=out)
         return out.view(B, N, D)
 
 
@@ -301,11 +351,12 @@ class PatchEmbedEngine:
             raise ValueError(f"sequence of {N} tokens exceeds the positional table ({pos.shape[0]})")
         dev = img.device
         a0 = torch.empty(B * n, t["kp"], device=dev, dtype=torch.bfloat16)
-        _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw)
+        _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw, eps=o.to_patch_embedding[1].eps)
         y = torch.empty(B * n, D, device=dev, dtype=torch.float32)
         _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
         x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
-        _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls, xb=xb, stats=stats)
+        _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls, xb=xb, stats=stats,
+                          eps=o.to_patch_embedding[3].eps)
         return x, B, N
 
     def geometry(self, img: torch.Tensor) -> Tuple[int, int]:

@@ -4,6 +4,8 @@
     for host_batch in loader:                    # pinned host tensors
         x = feeder.push(host_batch)              # device tensor, valid on the current stream
         logits = model(x)
+        feeder.done(x)                           # REQUIRED: marks the buffer free once the forward has read it --
+                                                 # without it the copy of batch i+2 may overwrite x under the forward
 
 Two device buffers and a dedicated copy stream; the compute stream only ever waits on the event of the copy it is
 about to consume, and a buffer is not overwritten before the forward that read it has finished.

@@ -10,10 +10,11 @@ Two executions of the same arithmetic:
     like the reference.
   * fused sm_100a path (CUDA bf16, eval, no autograd): images never interact, so the packing and the O(B L^2) mask are
     dropped altogether -- all tokens of all images form ONE padding-free [T, D] matrix described by cu_seqlens, the
-    encoder GEMMs run on it unchanged, attention is the varlen block-diagonal kernel (`b200vit_attention_varlen`, key
-    blocks of 128, any image size), q/k RMSNorm and the attention pooling are their own small kernels.  Patch
-    extraction ('c (h p1) (w p2) -> (h w) (c p1 p2)' per image) stays torch glue on the device: it is host-side packing
-    logic in the reference too (na_vit.py:288-325).
+    encoder GEMMs run on it unchanged, attention is the varlen block-diagonal kernel (`b200vit_attention_varlen`,
+    pipelined 64-key blocks, any image size), the q/k RMSNorm is an epilogue of the QKV GEMM and the attention pooling
+    its own small kernel.  Patch extraction ('c (h p1) (w p2) -> (h w) (c p1 p2)' per image, na_vit.py:300) + the
+    first LayerNorm is one kernel over the whole list of images (`b200vit_patchify_varlen_ln`), the positional rows
+    are gathered by `b200vit_embed_varlen`; the host only builds the small index arrays (`_lib.VarlenIndex`).
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import _lib
-from .engine import hooks_inside, ln_mode, why_not_fused
+from .engine import FusedWeightsMixin, _version_key, hooks_inside, ln_mode, on_device, why_not_fused
 
 
 def group_images_by_max_seq_len(images: Sequence[Tensor], patch_size: int,
@@ -134,7 +135,7 @@ class Transformer(nn.Module):
         return self.norm(x)
 
 
-class NaViT(nn.Module):
+class NaViT(FusedWeightsMixin, nn.Module):
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, channels=3, dim_head=64,
                  dropout=0., emb_dropout=0., token_dropout_prob=None) -> None:
         super().__init__()
@@ -178,6 +179,17 @@ class NaViT(nn.Module):
             return "depth == 0"
         p_drop = max(self.dropout.p, attn0.dropout_p)
         r = why_not_fused(list(self.parameters()), first, training=self.training, dropout_p=p_drop)
+        if r is None:
+            flat = batched_images if torch.is_tensor(batched_images[0]) else [im for row in batched_images for im in row]
+            for im in flat:
+                if not (torch.is_tensor(im) and im.is_cuda and im.device == first.device and im.dtype == first.dtype):
+                    r = "images differ in device or dtype"
+                    break
+                if torch.is_grad_enabled() and im.requires_grad:
+                    r = "autograd is recording (fused path is forward only)"
+                    break
+        if r is None and self._nonzero_beta():
+            r = "a LayerNorm `beta` buffer is non-zero (the fused path folds beta = 0, as the reference registers it)"
         if r is None and self.training and self.calc_token_dropout is not None:
             r = "token dropout is active"
         if r is None and hooks_inside(self, skip=(self.to_latent,)):
@@ -188,9 +200,18 @@ class NaViT(nn.Module):
             r = "dim / patch_dim not multiples of 8"
         return r
 
+    def _nonzero_beta(self) -> bool:
+        """The `beta` buffers are part of the state_dict; the fused path assumes the zeros the reference registers
+        (checked once per buffer version, not per forward: the check synchronises)."""
+        betas = [b for n, b in self.named_buffers() if n.endswith("beta")]
+        key = _version_key(betas)
+        if getattr(self, "_beta_key", None) != key:
+            self._beta_key, self._beta_nonzero = key, any(bool(b.any()) for b in betas)
+        return self._beta_nonzero
+
     def _prepared(self) -> Dict[str, Tensor]:
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = _version_key(params)
         if getattr(self, "_prep_key", None) == key:
             return self._prep
         f32 = lambda t: t.detach().float().contiguous()
@@ -247,10 +268,15 @@ class NaViT(nn.Module):
         heads = self.attn_pool.heads
         D = t["pos_h"].shape[1]
         I = t["0.a.out"].shape[1]
+        max_gh, max_gw = self.pos_embed_height.shape[0], self.pos_embed_width.shape[0]
         for img in images:
             assert img.ndim == 3 and img.shape[0] == c
             hh, ww = img.shape[-2:]
             assert hh % p == 0 and ww % p == 0, f'height and width {(hh, ww)} of images must be divisible by patch size {p}'
+            if hh < p or ww < p:
+                raise ValueError(f"image of {(hh, ww)} pixels has no {p} x {p} patch")
+            if hh // p > max_gh or ww // p > max_gw:     # the reference's table lookup raises here (na_vit.py:354-359)
+                raise IndexError(f"image of {(hh // p, ww // p)} patches exceeds the positional tables {(max_gh, max_gw)}")
         images = [im.contiguous() for im in images]
         # ---- host-side bookkeeping only: per-image token counts / grid shapes -> one small index buffer on the device;
         #      patch pixels and positional rows are gathered by the kernels
@@ -339,8 +365,16 @@ class NaViT(nn.Module):
                 group_max_seq_len: int = 2048) -> Tensor:
         if self.fused_reason(batched_images) is None:
             # grouping only decides which images share a padded row; the padding-free path does not need it, and the
-            # output order (input order) is the same either way
-            return self.forward_fused(batched_images)
+            # output order (input order) is the same either way -- except for the reference's size assertion
+            if group_images:
+                flat = batched_images if torch.is_tensor(batched_images[0]) else [im for r in batched_images for im in r]
+                for im in flat:
+                    n = (im.shape[-2] // self.patch_size) * (im.shape[-1] // self.patch_size)
+                    assert n <= group_max_seq_len, \
+                        f'image with dimensions {tuple(im.shape[-2:])} exceeds maximum sequence length'
+            first = batched_images[0] if torch.is_tensor(batched_images[0]) else batched_images[0][0]
+            with on_device(first):
+                return self.forward_fused(batched_images)
         return self.forward_eager(batched_images, group_images, group_max_seq_len)
 
     def forward_eager(self, batched_images: Union[List[Tensor], List[List[Tensor]]], group_images: bool = False,

@@ -14,7 +14,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode, why_not_fused
+from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode,
+                     on_device, why_not_fused)
 from .vit import Patchify, pair
 
 
@@ -73,7 +74,7 @@ class Attention(nn.Module):
         return self.to_out(out)
 
 
-class Transformer(nn.Module):
+class Transformer(FusedWeightsMixin, nn.Module):
     def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int) -> None:
         super().__init__()
         self.dropout_p = 0.0
@@ -115,7 +116,7 @@ class Transformer(nn.Module):
         return self.forward_eager(x)
 
 
-class SimpleViT(nn.Module):
+class SimpleViT(FusedWeightsMixin, nn.Module):
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, channels=3,
                  dim_head=64) -> None:
         super().__init__()
@@ -147,6 +148,8 @@ class SimpleViT(nn.Module):
     def fused_reason(self, img: torch.Tensor) -> Optional[str]:
         if img.dim() != 4:
             return "input is not (B, C, H, W)"
+        if img.shape[1] * self.patch_size[0] * self.patch_size[1] != self.to_patch_embedding[1].normalized_shape[0]:
+            return "channel count differs from the constructor's (the reference's LayerNorm raises)"
         if len(self.transformer.layers) == 0:
             return "depth == 0"
         r = why_not_fused(list(self.parameters()), img, training=self.training, dropout_p=0.0)
@@ -164,7 +167,8 @@ class SimpleViT(nn.Module):
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         if self.fused_reason(img) is None:
-            return self.forward_fused(img)
+            with on_device(img):
+                return self.forward_fused(img)
         return self.forward_eager(img)
 
     def forward_eager(self, img: torch.Tensor) -> torch.Tensor:

@@ -20,7 +20,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode, why_not_fused
+from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode,
+                     on_device, why_not_fused)
 
 
 def pair(t):
@@ -98,7 +99,7 @@ class Attention(nn.Module):
         return self.to_out(out)
 
 
-class Transformer(nn.Module):
+class Transformer(FusedWeightsMixin, nn.Module):
     """depth x (attention, feed-forward) residual blocks + final LayerNorm (reference vit.py:66-83).
 
     Callable on arbitrary (B, N, D) tokens, as the reference's MAE / SimMIM / distillation wrappers do.
@@ -146,7 +147,7 @@ class Transformer(nn.Module):
         return self.forward_eager(x)
 
 
-class ViT(nn.Module):
+class ViT(FusedWeightsMixin, nn.Module):
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, pool='cls', channels=3,
                  dim_head=64, dropout=0., emb_dropout=0.) -> None:
         super().__init__()
@@ -182,6 +183,8 @@ class ViT(nn.Module):
         """None if forward(img) will run the fused sm_100a kernels, else the reason for the PyTorch graph."""
         if img.dim() != 4:
             return "input is not (B, C, H, W)"
+        if img.shape[1] * self.patch_size[0] * self.patch_size[1] != self.to_patch_embedding[1].normalized_shape[0]:
+            return "channel count differs from the constructor's (the reference's LayerNorm raises)"
         if len(self.transformer.layers) == 0:
             return "depth == 0"
         p_drop = max(self._emb_dropout_p, self.transformer.dropout_p)
@@ -198,7 +201,8 @@ class ViT(nn.Module):
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         if self.fused_reason(img) is None:
-            return self.forward_fused(img)
+            with on_device(img):
+                return self.forward_fused(img)
         return self.forward_eager(img)
 
     # ---------------------------------------------------------------------------------------------- PyTorch graph
