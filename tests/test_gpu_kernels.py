@@ -173,7 +173,8 @@ def test_rowstats_cast():
     assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-5, atol=1e-3)
 
 
-@pytest.mark.parametrize("M,N,K", [(2048, 768, 768), (1300, 1024, 512)])
+@pytest.mark.parametrize("M,N,K", [(2048, 768, 768), (1300, 1024, 512),
+                                   (1536, 384, 384), (1100, 320, 2304)])   # last N tile only partly valid (ViT-S dims)
 def test_gemm_pair_kernel_dual_epilogue(M, N, K):
     """CTA-pair kernel, LN-fold producer epilogue: fp32 stream in place + bf16 copy + row statistics."""
     torch.manual_seed(M)

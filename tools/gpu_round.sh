@@ -22,7 +22,7 @@ PY
   tail -3 gpurun_out/bench_${TAG}_$m.err
 done
 if [ "${NCU:-1}" = "1" ]; then
-echo "== ncu launch list"
+[ "${NCU_LIST:-1}" = "1" ] && echo "== ncu launch list" && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-eager > gpurun_out/ncu_bench_${TAG}.log 2>&1
 tail -3 gpurun_out/launches_${TAG}.csv | cut -c1-300
 echo "== ncu full"

@@ -19,7 +19,13 @@
 // ceil(N/128) query tiles are consecutive pipeline tiles.  K/V ring of 3 stages + Q ring of 3 tiles: at the target
 // rate the kernel moves ~5.7 TB/s, so one whole unit has to be in flight from HBM while another is computed on.
 //
-// Roles: warps 0-3 softmax / epilogue (thread = query row), warp 4 TMA producer, warp 5 MMA issuer + TMEM allocator.
+// Softmax parallelism: ONE warp per SM sub-partition cannot hide its own instruction latencies (measured: 25 % issue
+// utilisation, MUFU 28 % busy, 3.2 us per tile; profiles/r02a).  So a score tile is worked on by 16 warps: warp w owns
+// TMEM lanes 32 (w % 4) ... +31 (hardware rule) = 32 query rows, and the four warps of a row quadrant split the KEY
+// columns in 16-column chunks (part = w / 4).  Row max and row sum are combined through shared memory with one
+// named barrier per quadrant and tile; the O read-out is split the same way (16 of the 64 columns per warp).
+//
+// Roles: warps 0-15 softmax / epilogue, warp 16 TMA producer, warp 17 MMA issuer + TMEM allocator.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -30,7 +36,8 @@ constexpr int DH = 64;
 constexpr int KV_STAGES = 3;
 constexpr int Q_SLOTS = 3;
 constexpr int Q_TILE_BYTES = 128 * 128;
-constexpr int THREADS = 6 * 32;
+constexpr int SM_WARPS = 16;            // softmax warps: 4 row quadrants x 4 column parts
+constexpr int THREADS = (SM_WARPS + 2) * 32;
 constexpr int MAX_KP = 224;  // 2 * KP + 64 <= 512 TMEM columns
 }  // namespace ap
 
@@ -72,10 +79,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* o_full = p_ready + 2;            // [1]
   uint64_t* o_free = o_full + 1;             // [1]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+  float* pmax = reinterpret_cast<float*>(tmem_base_smem + 4);  // [2 tile parities][4 parts][128 rows]
+  float* psum = pmax + 2 * 4 * 128;                            // [2][4][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int TMA_WARP = 4, MMA_WARP = 5;
+  constexpr int TMA_WARP = SM_WARPS, MMA_WARP = SM_WARPS + 1;
 
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -90,10 +99,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     for (int r = 0; r < 2; ++r) {
       mbar_init(&s_full[r], 1);
-      mbar_init(&p_ready[r], 4);
+      mbar_init(&p_ready[r], SM_WARPS);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
+    mbar_init(o_free, SM_WARPS);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -180,157 +189,158 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax / epilogue warpgroup
-    const int quad = warp;
+    // ---------------------------------------------------------------- softmax / epilogue warps
+    const int quad = warp & 3;   // TMEM lane quadrant = 32 query rows
+    const int part = warp >> 2;  // which share of the key columns (and of the 64 output columns)
     const int r_in_tile = quad * 32 + lane;
     const float c = p.scale_log2e;
-    const int nfull = p.N >> 5;  // 32-column chunks that need no key mask; the rest (< 48 columns): 16 at a time
+    const int nch = p.KP >> 4;  // 16-column chunks, dealt to the four parts as evenly as possible
+    // (the extra chunks go to the LAST parts: a warp's 4th chunk, which is re-read from TMEM instead of being kept in
+    //  registers, then always lies in the upper half of the score columns, which P never overwrites -- see below)
+    const int extra_from = 4 - (nch & 3);
+    const int ch0 = part * (nch >> 2) + max(part - extra_from, 0);
+    const int ch1 = ch0 + (nch >> 2) + (part >= extra_from ? 1 : 0);
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    auto quad_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory"); };
 
-    // O(jj) / rowsum -> bf16 -> out[b, row, h*64 : h*64+64]
-    auto epilogue = [&](int jj, float sum, bool active) {
+    // O(jj)[:, 16 part .. +16] / rowsum -> bf16 -> out[b, row, h*64 + 16 part ...]
+    auto epilogue = [&](int jj, bool active) {
       const int i = jj / p.nq, t = jj - i * p.nq;
       const int u = blockIdx.x + i * gridDim.x;
       const int h = u % p.H, b = u / p.H;
       const int qrow = t * 128 + r_in_tile;
       mbar_wait(o_full, jj & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
+      uint32_t r[16];
       if (active) {
-        const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + O_COL;
-        tmem_ld_32x32b_x32(t_o, r0);
-        tmem_ld_32x32b_x32(t_o + 32, r1);
+        tmem_ld_32x32b_x16(tmem_base + lane_off + O_COL + part * 16, r);
         tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
       if (active && qrow < p.N) {
-        const float inv = 1.0f / sum;
-        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * DH);
+        const float* ps = psum + (jj & 1) * 512 + r_in_tile;  // the quadrant barrier of the next tile ordered these
+        const float inv = 1.0f / ((ps[0] + ps[128]) + (ps[256] + ps[384]));
+        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * DH + part * 16);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          op[q] = make_uint4(pack_bf16x2(__uint_as_float(r0[8 * q]) * inv, __uint_as_float(r0[8 * q + 1]) * inv),
-                             pack_bf16x2(__uint_as_float(r0[8 * q + 2]) * inv, __uint_as_float(r0[8 * q + 3]) * inv),
-                             pack_bf16x2(__uint_as_float(r0[8 * q + 4]) * inv, __uint_as_float(r0[8 * q + 5]) * inv),
-                             pack_bf16x2(__uint_as_float(r0[8 * q + 6]) * inv, __uint_as_float(r0[8 * q + 7]) * inv));
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          op[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(r1[8 * q]) * inv, __uint_as_float(r1[8 * q + 1]) * inv),
-                                 pack_bf16x2(__uint_as_float(r1[8 * q + 2]) * inv, __uint_as_float(r1[8 * q + 3]) * inv),
-                                 pack_bf16x2(__uint_as_float(r1[8 * q + 4]) * inv, __uint_as_float(r1[8 * q + 5]) * inv),
-                                 pack_bf16x2(__uint_as_float(r1[8 * q + 6]) * inv, __uint_as_float(r1[8 * q + 7]) * inv));
+        for (int q = 0; q < 2; ++q)
+          op[q] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv),
+                             pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv),
+                             pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv),
+                             pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv));
       }
     };
 
-    float sum_prev = 1.f;
     bool active_prev = false;
     for (int j = 0; j < n_tiles; ++j) {
       const int t = j % p.nq;
-      // warps whose 32 query rows all lie beyond N skip the arithmetic but keep the barrier protocol in lockstep
+      // quadrants whose 32 query rows all lie beyond N skip the arithmetic but keep every barrier in lockstep
       const bool active = t * 128 + quad * 32 < p.N;
-      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (j & 1) * p.KP;
+      const uint32_t t_lane = tmem_base + lane_off + (j & 1) * p.KP;
+      float* my_max = pmax + (j & 1) * 512 + part * 128 + r_in_tile;
+      float* my_sum = psum + (j & 1) * 512 + part * 128 + r_in_tile;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      float sum = 1.f;
-      if (active) {
-        uint32_t ra[32], rb[32];
-        // ---------------- pass 1: row max (4 independent chains of 3-input max; next chunk's tcgen05.ld in flight)
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#define AP_MAX32(R)                                                                           \
-  _Pragma("unroll") for (int jj = 0; jj < 32; jj += 8) {                                      \
-    m0 = max3(m0, __uint_as_float(R[jj]), __uint_as_float(R[jj + 1]));                        \
-    m1 = max3(m1, __uint_as_float(R[jj + 2]), __uint_as_float(R[jj + 3]));                    \
-    m2 = max3(m2, __uint_as_float(R[jj + 4]), __uint_as_float(R[jj + 5]));                    \
-    m3 = max3(m3, __uint_as_float(R[jj + 6]), __uint_as_float(R[jj + 7]));                    \
-  }
-        int ci = 0;
-        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
-        for (; ci + 1 < nfull; ci += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
-          AP_MAX32(ra)
-          tmem_ld_wait();
-          if (ci + 2 < nfull) tmem_ld_32x32b_x32(t_lane + (ci + 2) * 32, ra);
-          AP_MAX32(rb)
-        }
-        if (ci < nfull) {
-          tmem_ld_wait();
-          AP_MAX32(ra)
-        }
-        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
-          uint32_t r16[16];
-          tmem_ld_32x32b_x16(t_lane + c0, r16);
-          tmem_ld_wait();
+      // The warp's share of the score row is read from TMEM ONCE and kept in registers (3 chunks x 16 fp32).  That is
+      // a correctness matter: P is written over S (columns [8 ch, 8 ch + 8) for chunk ch), i.e. into columns other
+      // warps of the quadrant own -- the quadrant barrier below, passed only after every warp's loads have completed,
+      // makes that safe.  A 4th chunk (KP = 208 / 224 only) is re-read after the barrier instead: it sits at columns
+      // >= 144, beyond the [0, KP/2) range P occupies, so nobody overwrites it.
+      uint32_t sv[3][16];
+      const int my_n = ch1 - ch0;
+      const bool tail = my_n == 4;
+      const int tail_c0 = (ch0 + 3) * 16;
+      // key columns >= N (zero-filled K rows) become -inf right after the load: max ignores them, exp2 gives 0
+      auto mask16 = [&](uint32_t (&r)[16], int c0) {
+        if (c0 + 16 > p.N) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj)
-            if (c0 + jj < p.N) m0 = fmaxf(m0, __uint_as_float(r16[jj]));
+          for (int q = 0; q < 16; ++q)
+            if (c0 + q >= p.N) r[q] = 0xff800000u;
         }
-#undef AP_MAX32
-        const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
-        // ---------------- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S
+      };
+      auto max16 = [&](const uint32_t (&r)[16], float& m0, float& m1) {
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          m0 = max3(m0, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
+          m1 = max3(m1, __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+        }
+      };
+      if (active) {
+        // ---------------- row max over this warp's columns
+        float m0 = -INFINITY, m1 = -INFINITY;
+        if (tail) {  // the 4th chunk first, through the registers of chunk 0
+          tmem_ld_32x32b_x16(t_lane + tail_c0, sv[0]);
+          tmem_ld_wait();
+          mask16(sv[0], tail_c0);
+          max16(sv[0], m0, m1);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < my_n) tmem_ld_32x32b_x16(t_lane + (ch0 + k) * 16, sv[k]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k < my_n) {
+            mask16(sv[k], (ch0 + k) * 16);
+            max16(sv[k], m0, m1);
+          }
+        }
+        *my_max = fmaxf(m0, m1);
+      }
+      tc_fence_before();
+      quad_barrier();  // partial maxima (and the previous tile's partial sums) visible; every S load has completed
+      tc_fence_after();
+      float sum = 0.f;
+      if (active) {
+        const float* pm = pmax + (j & 1) * 512 + r_in_tile;
+        const float mc = fmaxf(fmaxf(pm[0], pm[128]), fmaxf(pm[256], pm[384])) * c;
+        // ---------------- p = exp2(s*c - max*c), partial row sum, P (bf16 pairs) -> TMEM over S
         const f32x2 c2v = f2_make(c, c), nmc2v = f2_make(-mc, -mc);
         f32x2 acc0 = f2_make(0.f, 0.f), acc1 = f2_make(0.f, 0.f);
-#define AP_EXP32(R, C0)                                                                                   \
-  {                                                                                                       \
-    uint32_t pk[16];                                                                                      \
-    _Pragma("unroll") for (int jj = 0; jj < 32; jj += 4) {                                                \
-      float x0, x1, x2, x3;                                                                               \
-      f2_get(f2_fma(f2_make(__uint_as_float(R[jj]), __uint_as_float(R[jj + 1])), c2v, nmc2v), x0, x1);     \
-      f2_get(f2_fma(f2_make(__uint_as_float(R[jj + 2]), __uint_as_float(R[jj + 3])), c2v, nmc2v), x2, x3); \
-      const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);             \
-      acc0 = f2_add(acc0, f2_make(e0, e1));                                                               \
-      acc1 = f2_add(acc1, f2_make(e2, e3));                                                               \
-      pk[jj >> 1] = pack_bf16x2(e0, e1);                                                                  \
-      pk[(jj >> 1) + 1] = pack_bf16x2(e2, e3);                                                            \
-    }                                                                                                     \
-    tmem_st_32x32b_x16(t_lane + ((C0) >> 1), pk);                                                         \
-  }
-        ci = 0;
-        if (nfull > 0) tmem_ld_32x32b_x32(t_lane, ra);
-        for (; ci + 1 < nfull; ci += 2) {
+        auto exp16 = [&](const uint32_t (&r)[16], int c0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            float x0, x1, x2, x3;
+            f2_get(f2_fma(f2_make(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), c2v, nmc2v), x0, x1);
+            f2_get(f2_fma(f2_make(__uint_as_float(r[q + 2]), __uint_as_float(r[q + 3])), c2v, nmc2v), x2, x3);
+            const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);
+            acc0 = f2_add(acc0, f2_make(e0, e1));
+            acc1 = f2_add(acc1, f2_make(e2, e3));
+            pk[q >> 1] = pack_bf16x2(e0, e1);
+            pk[(q >> 1) + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk);
+        };
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < my_n) exp16(sv[k], (ch0 + k) * 16);
+        if (tail) {  // (re-read: columns >= 144 are never overwritten by P)
+          tmem_ld_32x32b_x16(t_lane + tail_c0, sv[0]);
           tmem_ld_wait();
-          tmem_ld_32x32b_x32(t_lane + (ci + 1) * 32, rb);
-          AP_EXP32(ra, ci * 32)
-          tmem_ld_wait();
-          if (ci + 2 < nfull) tmem_ld_32x32b_x32(t_lane + (ci + 2) * 32, ra);
-          AP_EXP32(rb, (ci + 1) * 32)
+          mask16(sv[0], tail_c0);
+          exp16(sv[0], tail_c0);
         }
-        if (ci < nfull) {
-          tmem_ld_wait();
-          AP_EXP32(ra, ci * 32)
-        }
-#undef AP_EXP32
         float s0, s1, s2, s3;
         f2_get(acc0, s0, s1);
         f2_get(acc1, s2, s3);
-        for (int c0 = nfull * 32; c0 < p.KP; c0 += 16) {
-          uint32_t r16[16];
-          tmem_ld_32x32b_x16(t_lane + c0, r16);
-          tmem_ld_wait();
-          uint32_t pk8[8];
-#pragma unroll
-          for (int jj = 0; jj < 16; jj += 2) {
-            const float e0 = (c0 + jj < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[jj]), c, -mc)) : 0.f;
-            const float e1 = (c0 + jj + 1 < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[jj + 1]), c, -mc)) : 0.f;
-            s0 += e0;
-            s1 += e1;
-            pk8[jj >> 1] = pack_bf16x2(e0, e1);
-          }
-          tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk8);
-        }
         sum = (s0 + s1) + (s2 + s3);
         tmem_st_wait();
       }
+      *my_sum = sum;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[j & 1]);
 
       // O of the PREVIOUS tile: its PV ran while this tile's softmax was computed
-      if (j > 0) epilogue(j - 1, sum_prev, active_prev);
-      sum_prev = sum;
+      if (j > 0) epilogue(j - 1, active_prev);
       active_prev = active;
     }
-    if (n_tiles > 0) epilogue(n_tiles - 1, sum_prev, active_prev);
+    if (n_tiles > 0) {
+      quad_barrier();  // the last tile's partial sums
+      epilogue(n_tiles - 1, active_prev);
+    }
   }
 
   tc_fence_before();
@@ -375,7 +385,7 @@ int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float
     if (rc) return rc;
   }
   const size_t smem_bytes = (size_t)KV_STAGES * 2 * p.kv_bytes + (size_t)Q_SLOTS * Q_TILE_BYTES +
-                            (2 * KV_STAGES + 2 * Q_SLOTS + 6) * 8 + 16 + 1024;
+                            (2 * KV_STAGES + 2 * Q_SLOTS + 6) * 8 + 16 + 2 * 2 * 4 * 128 * sizeof(float) + 1024;
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   B200_ENSURE_SMEM(attention_pipe_kernel, smem_bytes);
   const int grid = p.units < num_sms() ? p.units : num_sms();

@@ -482,6 +482,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (DUAL) {
               // bf16 copy of the new residual rows (A operand of the next, LN-folded GEMM) + its row statistics
               const int half = (c >> 5) & 1;
+              const uint32_t nmask = (n_blk * BLOCK_N + col_off + c < p.N) ? 0xFFFFFFFFu : 0u;
               if (half == 0) mbar_wait(&bbuf_free[e], ((box_seq >> 1) & 1) ^ 1);  // previous pair's store has read it
               const uint32_t brow_s = smem_u32(bbuf) + lane * 128;
 #pragma unroll
@@ -492,7 +493,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
                 pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
                 sts_v4(brow_s + ((static_cast<uint32_t>(half * 4 + q) ^ sw) << 4), pk.x, pk.y, pk.z, pk.w);
-                const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+                // (columns at or beyond N -- a last tile of 64 / 128 / 192 valid columns -- are clipped by the TMA
+                //  stores; they must not reach the statistics either: masked to +0, which leaves the sums bit-exact)
+                const uint32_t w4[4] = {pk.x & nmask, pk.y & nmask, pk.z & nmask, pk.w & nmask};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float lo = __uint_as_float(w4[i] << 16);
@@ -512,14 +515,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&out_bar[box_seq & 1]);  // the TMA lane stores it and recycles the buffer
           ++box_seq;
+          if (DUAL && EPI_WARPS == 4 && c == 96) {  // end of the tile's first 128 columns: their statistics slot
+            if (row_ok)
+              *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + n_blk * 2)) =
+                  make_float2(st_sum, st_sq);
+            st_sum = st_sq = 0.f;
+          }
         }
         if (DUAL && row_ok) {
-          // one statistics slot per 128 output columns: with 8 warps each column half of the tile has its own warp,
-          // with 4 warps this warp covered both halves (the second slot is written as zero)
-          const int part = n_blk * 2 + (e >> 2);
-          float2* sp = reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part));
-          sp[0] = make_float2(st_sum, st_sq);
-          if (EPI_WARPS == 4 && part + 1 < p.stats_parts) sp[1] = make_float2(0.f, 0.f);
+          // one statistics slot per 128 output columns (the same association of the partial sums whichever kernel
+          // variant produced them: results do not depend on the batch size).  With 8 warps each column half of the
+          // tile has its own warp; with 4 warps the first half was written inside the loop above.
+          const int part = n_blk * 2 + (EPI_WARPS == 4 ? 1 : (e >> 2));
+          if (part < p.stats_parts)
+            *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + part)) =
+                make_float2(st_sum, st_sq);
         }
         if (++acc == 2) {
           acc = 0;
