@@ -85,13 +85,15 @@ int b200vit_patchify_ln(const void* img, const float* gamma, const float* beta, 
  * Token assembly after the patch projection: y[B*n, D] (fp32, patch GEMM output incl. bias) ->
  *   x[b, t, :] = LN_D(y[b, t - ncls, :]) * gamma + beta + pos[t, :]   for t >= ncls
  *   x[b, 0, :] = cls[:] + pos[0, :]                                    if ncls == 1
- * written as the fp32 residual stream x[B*(n+ncls), D].  Optional (may be NULL): xb_bf16 = bf16 copy of x and
+ *   x[b, ncls + n + r, :] = tail[r, :]                                 for r < ntail (register tokens, no pos;
+ *                                                                       simple_vit_with_register_tokens.py:124-126)
+ * written as the fp32 residual stream x[B*(ncls+n+ntail), D].  Optional (may be NULL): xb_bf16 = bf16 copy of x and
  * stats[M][2] = per-row (sum, sum of squares) of that copy -- the inputs of the first LN-folded GEMM.
  * Replaces nn.LayerNorm(dim) vit.py:103, cls concat vit.py:122-123, pos add vit.py:125-127 (simple_vit.py:94,114).
  */
 int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls, const float* pos,
-                         float* x, void* xb_bf16, float* stats, int B, int n, int ncls, int D, float eps,
-                         void* stream);
+                         const float* tail, float* x, void* xb_bf16, float* stats, int B, int n, int ncls, int ntail,
+                         int D, float eps, void* stream);
 
 /* x[M, D] fp32 -> xb bf16 copy + stats[M][2] = (sum, sum of squares) of the bf16-rounded rows: entry into the
  * LN-folded layer chain for token matrices handed to Transformer.forward directly (reference mae.py:74). */
@@ -172,8 +174,9 @@ int b200vit_embed_varlen(const float* y, const float* gamma, const float* pos_h,
 int b200vit_attn_pool(const void* kv, const float* qn, const int32_t* cu_seqlens_dev, void* out, int S, int H, int dh,
                       void* stream);
 
-/* Mean over tokens: x[B, N, D] fp32 -> out[B, D] fp32 (vit.py:135 pool == 'mean', simple_vit.py:117). */
-int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream);
+/* Mean over the first n_pool tokens of every image: x[B, N, D] fp32 -> out[B, D] fp32 (vit.py:135 pool == 'mean',
+ * simple_vit.py:117: n_pool = N; simple_vit_with_register_tokens.py:130-132: the patch tokens only). */
+int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, int n_pool, void* stream);
 
 /* fp32 -> bf16 cast of a contiguous buffer of n elements (n multiple of 8). */
 int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);

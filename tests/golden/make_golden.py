@@ -45,10 +45,38 @@ CASES = {
                                         mlp_dim=256)),
 }
 
+# Round 2: attention without output projection (vit.py:34,46-49) and the SURVEY.md 8(f3) SimpleViT-family variants.
+# `kind` = module name inside the reference package for the variants.
+CASES2 = {
+    "vit_tiny_noproj": dict(kind="vit", seed=4, batch=3, img=(32, 32),
+                            kwargs=dict(image_size=32, patch_size=8, num_classes=7, dim=64, depth=2, heads=1,
+                                        dim_head=64, mlp_dim=128)),
+    "simplevit_registers": dict(kind="simple_vit_with_register_tokens", seed=6, batch=3, img=(32, 32),
+                                kwargs=dict(image_size=32, patch_size=4, num_classes=10, dim=128, depth=2, heads=2,
+                                            mlp_dim=256, num_register_tokens=4)),
+    "simplevit_qknorm": dict(kind="simple_vit_with_qk_norm", seed=7, batch=3, img=(32, 32),
+                             kwargs=dict(image_size=32, patch_size=4, num_classes=10, dim=128, depth=2, heads=2,
+                                         mlp_dim=256)),
+    "simplevit_patchdrop": dict(kind="simple_vit_with_patch_dropout", seed=8, batch=3, img=(32, 48),
+                                kwargs=dict(image_size=64, patch_size=8, num_classes=10, dim=128, depth=2, heads=2,
+                                            mlp_dim=256, patch_dropout=0.5)),
+    "simplevit_flash": dict(kind="simple_flash_attn_vit", seed=9, batch=3, img=(48, 32),
+                            kwargs=dict(image_size=64, patch_size=8, num_classes=10, dim=128, depth=2, heads=2,
+                                        mlp_dim=256, use_flash=True)),
+}
+
+
+def reference_class(kind: str):
+    """kind -> class of the UNMODIFIED reference."""
+    import importlib
+    if kind in ("vit", "simple"):
+        return ViT if kind == "vit" else SimpleViT
+    return importlib.import_module("vit_pytorch." + kind).SimpleViT
+
 
 def make(name: str, spec: dict) -> None:
     torch.manual_seed(spec["seed"])
-    cls = ViT if spec["kind"] == "vit" else SimpleViT
+    cls = reference_class(spec["kind"])
     model = cls(**spec["kwargs"]).eval()
     # bf16-representable parameters; perturb LayerNorm affine params so gamma/beta are actually exercised
     g = torch.Generator().manual_seed(1000 + spec["seed"])
@@ -58,6 +86,8 @@ def make(name: str, spec: dict) -> None:
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
             elif p.dim() == 1 and n.endswith("bias"):
                 p.add_(0.05 * torch.randn(p.shape, generator=g))
+            elif n.endswith("gamma"):                       # per-head q / k RMSNorm scales
+                p.mul_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
             p.copy_(p.bfloat16().float())
     torch.manual_seed(100 + spec["seed"])
     img = torch.randn(spec["batch"], 3, *spec["img"]).bfloat16()
@@ -147,7 +177,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "navit_config5":
         make_navit_config5()
         sys.exit(0)
-    for n, s in CASES.items():
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        for n, s in CASES2.items():
+            make(n, s)
+        sys.exit(0)
+    for n, s in {**CASES, **CASES2}.items():
         make(n, s)
     make_navit()
     make_navit_config5()

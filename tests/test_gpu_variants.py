@@ -1,0 +1,72 @@
+"""-m gpu: the SURVEY.md 8(f3) variants and attention without output projection through the fused sm_100a path, against
+the UNMODIFIED reference's fp32 logits (goldens) with the reference's own bf16 error as the pass criterion."""
+import importlib
+
+import pytest
+import torch
+
+from conftest import load_golden
+from vit_pytorch_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ALL = ["vit_tiny_noproj", "simplevit_registers", "simplevit_qknorm", "simplevit_patchdrop", "simplevit_flash"]
+
+
+def dropin_class(kind: str):
+    if kind == "vit":
+        from vit_pytorch_b200 import ViT
+        return ViT
+    return importlib.import_module("vit_pytorch_b200." + kind).SimpleViT
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("mode", ["fold", "exact"])
+def test_variant_fused_against_reference_golden(name, mode, monkeypatch):
+    monkeypatch.setenv("B200VIT_LN_MODE", mode)
+    g = load_golden(name)
+    m = dropin_class(g["kind"])(**g["kwargs"]).eval()
+    m.load_state_dict(g["state_dict"])
+    m = m.to(DEV, torch.bfloat16)
+    img = g["input"].to(DEV)
+    _lib.reset_launch_count()
+    with torch.inference_mode():
+        assert m.fused_reason(img) is None, m.fused_reason(img)
+        out = m(img)
+    assert _lib.launch_count() > 0
+    ref = g["logits_fp32"]
+    d = (out.float().cpu() - ref).abs()
+    floor = (g["logits_ref_bf16"] - ref).abs()
+    print(f"{name} [{mode}]: fused max {d.max():.5f} mean {d.mean():.5f}; reference-bf16 max {floor.max():.5f} "
+          f"mean {floor.mean():.5f}")
+    assert out.shape == ref.shape and torch.isfinite(out.float()).all()
+    # no worse than the reference's own bf16 forward on the same inputs (small slack on the max of a tiny sample)
+    assert d.mean() <= floor.mean() * 1.05 + 1e-4 and d.max() <= floor.max() * 1.5 + 1e-3
+
+
+def test_register_tokens_do_not_enter_the_pool():
+    """The mean runs over the patch tokens only: changing how many registers exist changes the logits only through
+    attention, and the fused result equals the model's own PyTorch graph."""
+    from vit_pytorch_b200.simple_vit_with_register_tokens import SimpleViT
+    torch.manual_seed(0)
+    m = SimpleViT(image_size=64, patch_size=8, num_classes=12, dim=128, depth=2, heads=2, mlp_dim=256,
+                  num_register_tokens=3).eval().to(DEV, torch.bfloat16)
+    img = torch.randn(5, 3, 64, 64, device=DEV).bfloat16()
+    with torch.inference_mode():
+        fused = m(img)
+        eager = m.float().forward_eager(img.float())
+    assert (fused.float() - eager).abs().max() < 2e-2
+
+
+def test_flash_variant_accepts_other_resolutions():
+    from vit_pytorch_b200.simple_flash_attn_vit import SimpleViT
+    torch.manual_seed(1)
+    m = SimpleViT(image_size=64, patch_size=8, num_classes=6, dim=128, depth=1, heads=2, mlp_dim=256).eval()
+    m = m.to(DEV, torch.bfloat16)
+    for hw in ((64, 64), (32, 48), (8, 8)):
+        img = torch.randn(2, 3, *hw, device=DEV).bfloat16()
+        with torch.inference_mode():
+            assert m.fused_reason(img) is None
+            fused = m(img)
+            eager = m.forward_eager(img)
+        assert (fused.float() - eager.float()).abs().max() < 3e-2

@@ -69,7 +69,7 @@ def lib() -> C.CDLL:
     L.b200vit_patchify_ln.restype = i32
     L.b200vit_patchify_ln.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_embed_tokens.restype = i32
-    L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_rowstats_cast.restype = i32
     L.b200vit_rowstats_cast.argtypes = [vp, vp, vp, i32, i32, vp]
     L.b200vit_debug_set.restype = i32
@@ -89,7 +89,7 @@ def lib() -> C.CDLL:
     L.b200vit_attn_pool.restype = i32
     L.b200vit_attn_pool.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.b200vit_mean_pool.restype = i32
-    L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.b200vit_cast_f32_bf16.restype = i32
     L.b200vit_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
     _lib = L
@@ -282,15 +282,19 @@ def patchify_ln(img: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_
 
 def embed_tokens(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, cls: Optional[torch.Tensor],
                  pos: torch.Tensor, x: torch.Tensor, B: int, n: int, ncls: int, eps: float = 1e-5,
-                 xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
+                 xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+                 tail: Optional[torch.Tensor] = None) -> None:
+    """tail [ntail, D]: rows appended after the n patch tokens of every image (register tokens, no pos)."""
     _chk(xb, torch.bfloat16, "xb"); _chk(stats, torch.float32, "stats")
-    for nm, t in (("y", y), ("gamma", gamma), ("beta", beta), ("cls", cls), ("pos", pos), ("x", x)):
+    for nm, t in (("y", y), ("gamma", gamma), ("beta", beta), ("cls", cls), ("pos", pos), ("x", x), ("tail", tail)):
         _chk(t, torch.float32, nm)
     D = y.shape[1]
-    assert y.is_contiguous() and x.is_contiguous() and pos.is_contiguous()
+    ntail = 0 if tail is None else tail.shape[0]
+    assert y.is_contiguous() and x.is_contiguous() and pos.is_contiguous() and (tail is None or tail.is_contiguous())
+    assert x.shape[0] == B * (n + ncls + ntail) and pos.shape[0] >= n + ncls
     with _Timed("embed_tokens", bytes=(y.numel() + x.numel()) * 4):
-        rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(x), _ptr(xb),
-                                        _ptr(stats), B, n, ncls, D, float(eps), _stream())
+        rc = lib().b200vit_embed_tokens(_ptr(y), _ptr(gamma), _ptr(beta), _ptr(cls), _ptr(pos), _ptr(tail), _ptr(x),
+                                        _ptr(xb), _ptr(stats), B, n, ncls, ntail, D, float(eps), _stream())
     _check(rc, "b200vit_embed_tokens")
 
 
@@ -437,11 +441,12 @@ def attn_pool(kv: torch.Tensor, qn: torch.Tensor, cu_seqlens: torch.Tensor, out:
     _check(rc, "b200vit_attn_pool")
 
 
-def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int) -> None:
+def mean_pool(x: torch.Tensor, out: torch.Tensor, B: int, N: int, D: int, n_pool: Optional[int] = None) -> None:
+    """out[b] = mean of the first n_pool (default: all N) token rows of image b."""
     _chk(x, torch.float32, "x"); _chk(out, torch.float32, "out")
     assert x.is_contiguous() and out.is_contiguous()
     with _Timed("mean_pool", bytes=x.numel() * 4):
-        rc = lib().b200vit_mean_pool(_ptr(x), _ptr(out), B, N, D, _stream())
+        rc = lib().b200vit_mean_pool(_ptr(x), _ptr(out), B, N, D, N if n_pool is None else int(n_pool), _stream())
     _check(rc, "b200vit_mean_pool")
 
 

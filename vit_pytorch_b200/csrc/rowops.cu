@@ -290,15 +290,15 @@ __global__ void __launch_bounds__(256)
 embed_tokens_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                     __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int B, int n, int ncls, int D,
-                    float eps) {
-  const int N = n + ncls;
+                    float eps, const float* __restrict__ tail, int ntail) {
+  const int N = n + ncls + ntail;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * N) return;
   const int b = (int)(row / N), t = (int)(row % N);
   float* xr = x + row * D;
   __nv_bfloat16* xbr = xb ? xb + row * D : nullptr;
-  const float* pr = pos + (long long)t * D;
+  const float* pr = pos + (long long)min(t, n + ncls - 1) * D;  // (tail rows carry no positional embedding)
   float s1 = 0.f, s2 = 0.f;  // sum / sum of squares of the bf16-rounded row (LN-fold statistics for the first layer)
   auto emit = [&](int i, float v) {
     xr[i] = v;
@@ -310,6 +310,8 @@ embed_tokens_kernel(const float* __restrict__ y, const float* __restrict__ gamma
   };
   if (t < ncls) {
     for (int i = lane; i < D; i += 32) emit(i, cls[(long long)t * D + i] + pr[i]);
+  } else if (t >= ncls + n) {  // register tokens appended after the patches (simple_vit_with_register_tokens.py:124-126)
+    for (int i = lane; i < D; i += 32) emit(i, tail[(long long)(t - ncls - n) * D + i]);
   } else {
     const float* yr = y + ((long long)b * n + (t - ncls)) * D;
     float mean, rstd;
@@ -391,14 +393,14 @@ rowstats_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-mean_pool_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int D) {
+mean_pool_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int D, int n_pool) {
   const int b = blockIdx.y;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   const float* xp = x + (long long)b * N * D + d;
   float s = 0.f;
-  for (int t = 0; t < N; ++t) s += xp[(long long)t * D];
-  out[(long long)b * D + d] = s / (float)N;
+  for (int t = 0; t < n_pool; ++t) s += xp[(long long)t * D];
+  out[(long long)b * D + d] = s / (float)n_pool;
 }
 
 __global__ void __launch_bounds__(256)
@@ -476,23 +478,25 @@ extern "C" int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats
 }
 
 extern "C" int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, const float* cls,
-                                    const float* pos, float* x, void* xb_bf16, float* stats, int B, int n, int ncls,
-                                    int D, float eps, void* stream) {
+                                    const float* pos, const float* tail, float* x, void* xb_bf16, float* stats, int B,
+                                    int n, int ncls, int ntail, int D, float eps, void* stream) {
   B200_CHECK_ARG(y && gamma && beta && pos && x, "embed_tokens: null pointer");
   B200_CHECK_ARG(ncls == 0 || cls, "embed_tokens: ncls=%d without cls", ncls);
-  B200_CHECK_ARG(B > 0 && n > 0 && D > 0 && ncls >= 0, "embed_tokens: bad shape");
-  const long long rows = (long long)B * (n + ncls);
+  B200_CHECK_ARG(ntail == 0 || tail, "embed_tokens: ntail=%d without tail", ntail);
+  B200_CHECK_ARG(B > 0 && n > 0 && D > 0 && ncls >= 0 && ntail >= 0, "embed_tokens: bad shape");
+  const long long rows = (long long)B * (n + ncls + ntail);
   embed_tokens_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      y, gamma, beta, cls, pos, x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, B, n, ncls, D, eps);
+      y, gamma, beta, cls, pos, x, reinterpret_cast<__nv_bfloat16*>(xb_bf16), stats, B, n, ncls, D, eps, tail, ntail);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-extern "C" int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, void* stream) {
+extern "C" int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, int n_pool, void* stream) {
   B200_CHECK_ARG(x && out && B > 0 && N > 0 && D > 0, "mean_pool: bad argument");
+  B200_CHECK_ARG(n_pool > 0 && n_pool <= N, "mean_pool: n_pool=%d outside (0, N=%d]", n_pool, N);
   dim3 grid((D + 255) / 256, B);
-  mean_pool_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, N, D);
+  mean_pool_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, N, D, n_pool);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -94,6 +94,11 @@ def why_not_fused(params: List[torch.Tensor], x: torch.Tensor, *, training: bool
     return None
 
 
+def _softmax_scale(attn) -> float:
+    """dim_head ** -0.5 (vit.py:37,57) unless the module says otherwise (q/k-normalised attention uses 1)."""
+    return float(getattr(attn, "softmax_scale", attn.scale))
+
+
 class _Prepared:
     """Flat device buffers derived from one module's parameters + the parameter versions they were built from."""
 
@@ -166,12 +171,14 @@ class TransformerEngine:
     def params(self) -> List[torch.Tensor]:
         return list(self.mod.parameters())
 
+    def has_final_norm(self) -> bool:
+        """simple_flash_attn_vit.py's Transformer has no final LayerNorm (its head carries one instead)."""
+        return getattr(self.mod, "norm", None) is not None
+
     def unsupported_reason(self, N: int) -> Optional[str]:
         for attn, ff in self._layers():
             if attn.dim_head != 64:
                 return f"dim_head={attn.dim_head} (the attention kernel is built for 64)"
-            if not attn.project_out:
-                return "attention without output projection (heads == 1 and dim_head == dim)"
             if attn.dim % 8 or ff.hidden_dim % 8:
                 return "dim / mlp_dim not multiples of 8"
         if N > 16384:
@@ -200,14 +207,24 @@ class TransformerEngine:
             t[f"{i}.qkv.w"] = _bf16_rows(attn.to_qkv.weight)
             fold(f"{i}.qkv", attn.to_qkv.weight, None, attn.norm.weight, attn.norm.bias)
             fold(f"{i}.fc1", ff.parts()[1].weight, ff.parts()[1].bias, ff.parts()[0].weight, ff.parts()[0].bias)
-            out_lin = attn.out_linear()
-            t[f"{i}.out.w"] = _bf16_rows(out_lin.weight)
-            t[f"{i}.out.b"] = _f32(out_lin.bias) if out_lin.bias is not None else None
+            out_lin = attn.out_linear() if getattr(attn, "project_out", True) else None
+            if out_lin is None:
+                # reference vit.py:34,46-49: heads == 1 and dim_head == dim -> to_out is nn.Identity.  The residual
+                # GEMM then runs with an identity weight: bf16 x 1.0 products accumulate exactly, so x += o bit for bit
+                t[f"{i}.out.w"] = torch.eye(attn.dim, device=attn.to_qkv.weight.device, dtype=torch.bfloat16)
+                t[f"{i}.out.b"] = None
+            else:
+                t[f"{i}.out.w"] = _bf16_rows(out_lin.weight)
+                t[f"{i}.out.b"] = _f32(out_lin.bias) if out_lin.bias is not None else None
+            if getattr(attn, "q_norm", None) is not None:
+                # per-head q / k RMSNorm (simple_vit_with_qk_norm.py:29-37,60-67): epilogue of the QKV GEMM
+                t[f"{i}.gqk"] = torch.cat([_f32(attn.q_norm.gamma).reshape(-1), _f32(attn.k_norm.gamma).reshape(-1)])
             ln, fc1, fc2 = ff.parts()
             t[f"{i}.ln2.w"], t[f"{i}.ln2.b"] = _f32(ln.weight), _f32(ln.bias)
             t[f"{i}.fc1.w"], t[f"{i}.fc1.b"] = _bf16_rows(fc1.weight), _f32(fc1.bias)
             t[f"{i}.fc2.w"], t[f"{i}.fc2.b"] = _bf16_rows(fc2.weight), _f32(fc2.bias)
-        t["norm.w"], t["norm.b"] = _f32(self.mod.norm.weight), _f32(self.mod.norm.bias)
+        if self.has_final_norm():
+            t["norm.w"], t["norm.b"] = _f32(self.mod.norm.weight), _f32(self.mod.norm.bias)
         self.prep.key, self.prep.t = key, t
         return t
 
@@ -236,14 +253,14 @@ class TransformerEngine:
     def _attention(self, ws: Dict[str, torch.Tensor], B: int, N: int, attn) -> None:
         """Single-pass kernel for N <= 512 keys, the key-block (varlen) kernel beyond."""
         if N <= 512:
-            _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, attn.scale)
+            _lib.attention(ws["qkv"], ws["o"], B, N, attn.heads, attn.dim_head, _softmax_scale(attn))
             return
         key = (B, N, ws["qkv"].device)
         if getattr(self, "_vl_key", None) != key:
             self._vl = _lib.varlen_index([N] * B, ws["qkv"].device)
             self._vl_key = key
         cu, tp, tiles = self._vl
-        _lib.attention_varlen(ws["qkv"], ws["o"], cu, tp, tiles, attn.heads, attn.dim_head, attn.scale)
+        _lib.attention_varlen(ws["qkv"], ws["o"], cu, tp, tiles, attn.heads, attn.dim_head, _softmax_scale(attn))
 
     def run_blocks(self, x: torch.Tensor, B: int, N: int, primed: bool = False) -> None:
         """All encoder layers, in place on the fp32 residual stream x[B*N, D] (no final LayerNorm).
@@ -258,8 +275,13 @@ class TransformerEngine:
             if not primed:
                 _lib.rowstats_cast(x, xb, ws["stats_in"])
             for i, (attn, ff) in enumerate(self._layers()):
-                _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
-                          ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"], ln_eps=attn.norm.eps)
+                if f"{i}.gqk" in t:
+                    _lib.gemm_headnorm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
+                                       ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"],
+                                       ln_eps=attn.norm.eps, head_gamma=t[f"{i}.gqk"], norm_heads=2 * attn.heads)
+                else:
+                    _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
+                              ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"], ln_eps=attn.norm.eps)
                 self._attention(ws, B, N, attn)
                 _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
                           stats_out=sb)
@@ -270,7 +292,11 @@ class TransformerEngine:
             return
         for i, (attn, ff) in enumerate(self._layers()):
             _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"], eps=attn.norm.eps)
-            _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
+            if f"{i}.gqk" in t:
+                _lib.gemm_headnorm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"], head_gamma=t[f"{i}.gqk"],
+                                   norm_heads=2 * attn.heads)
+            else:
+                _lib.gemm(ws["xn"], t[f"{i}.qkv.w"], out_bf16=ws["qkv"])
             self._attention(ws, B, N, attn)
             _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, bias=t[f"{i}.out.b"], resid=x)
             _lib.layernorm(x, t[f"{i}.ln2.w"], t[f"{i}.ln2.b"], out_bf16=ws["xn"], eps=ff.parts()[0].eps)
@@ -280,6 +306,7 @@ class TransformerEngine:
     def final_norm(self, x: torch.Tensor, *, out_bf16: Optional[torch.Tensor] = None,
                    out_f32: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None) -> None:
         t = self.prepared()
+        assert self.has_final_norm()
         _lib.layernorm(x, t["norm.w"], t["norm.b"], out_bf16=out_bf16, out_f32=out_f32, row_index=row_index,
                        eps=self.mod.norm.eps)
 
@@ -291,7 +318,10 @@ class TransformerEngine:
             x = tokens.reshape(B * N, D).float().contiguous()
             self.run_blocks(x, B, N)
             out = torch.empty(B * N, D, device=tokens.device, dtype=torch.bfloat16)
-            self.final_norm(x, out_bf16=out)
+            if self.has_final_norm():
+                self.final_norm(x, out_bf16=out)
+            else:
+                _lib.cast_f32_bf16(x.view(-1), out.view(-1))
         return out.view(B, N, D)
 
 
@@ -305,7 +335,7 @@ class PatchEmbedEngine:
     def params(self) -> List[torch.Tensor]:
         o = self.owner
         ps = list(o.to_patch_embedding.parameters())
-        for name in ("cls_token", "pos_embedding"):
+        for name in ("cls_token", "pos_embedding", "register_tokens"):
             v = getattr(o, name, None)
             if isinstance(v, nn.Parameter):
                 ps.append(v)
@@ -328,10 +358,23 @@ class PatchEmbedEngine:
         t["kp"] = kp  # type: ignore[assignment]
         cls = getattr(o, "cls_token", None)
         t["cls"] = _f32(cls) if (cls is not None and cls.shape[0] > 0) else None
-        pos = o.pos_embedding
-        t["pos"] = pos.detach().to(device=device, dtype=torch.float32).contiguous()
+        reg = getattr(o, "register_tokens", None)          # simple_vit_with_register_tokens.py:103,124-126
+        t["tail"] = _f32(reg) if (reg is not None and reg.shape[0] > 0) else None
+        pos = getattr(o, "pos_embedding", None)
+        t["pos"] = pos.detach().to(device=device, dtype=torch.float32).contiguous() if pos is not None else None
         self.prep.key, self.prep.t = key, t
         return t
+
+    def _pos_table(self, t: Dict[str, torch.Tensor], gh: int, gw: int, device: torch.device) -> torch.Tensor:
+        """The module's positional table, or -- for the variants that build the sin-cos table from the input's own
+        patch grid on every call (simple_flash_attn_vit.py:158-160) -- that table, cached per grid shape."""
+        if t["pos"] is not None:
+            return t["pos"]
+        cache = self.__dict__.setdefault("_pos_cache", {})
+        key = (gh, gw, str(device))
+        if key not in cache:
+            cache[key] = self.owner.fused_pos_table(gh, gw).to(device=device, dtype=torch.float32).contiguous()
+        return cache[key]
 
     def run(self, img: torch.Tensor, xb: Optional[torch.Tensor] = None,
             stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:
@@ -344,11 +387,12 @@ class PatchEmbedEngine:
         t = self.prepared(img.device)
         n = (H // ph) * (W // pw)
         ncls = 0 if t["cls"] is None else t["cls"].shape[0]
-        N = n + ncls
+        ntail = 0 if t["tail"] is None else t["tail"].shape[0]
+        N = n + ncls + ntail
         D = t["w"].shape[0]
-        pos = t["pos"]
-        if pos.shape[0] < N:
-            raise ValueError(f"sequence of {N} tokens exceeds the positional table ({pos.shape[0]})")
+        pos = self._pos_table(t, H // ph, W // pw, img.device)
+        if pos.shape[0] < n + ncls:
+            raise ValueError(f"sequence of {n + ncls} tokens exceeds the positional table ({pos.shape[0]})")
         dev = img.device
         a0 = torch.empty(B * n, t["kp"], device=dev, dtype=torch.bfloat16)
         _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw, eps=o.to_patch_embedding[1].eps)
@@ -356,15 +400,16 @@ class PatchEmbedEngine:
         _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
         x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
         _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls, xb=xb, stats=stats,
-                          eps=o.to_patch_embedding[3].eps)
+                          eps=o.to_patch_embedding[3].eps, tail=t["tail"])
         return x, B, N
 
     def geometry(self, img: torch.Tensor) -> Tuple[int, int]:
         """(B, N) the image batch will produce, without running anything."""
         ph, pw = self.owner.patch_size
         cls = getattr(self.owner, "cls_token", None)
-        ncls = cls.shape[0] if cls is not None else 0
-        return img.shape[0], (img.shape[2] // ph) * (img.shape[3] // pw) + ncls
+        reg = getattr(self.owner, "register_tokens", None)
+        extra = (cls.shape[0] if cls is not None else 0) + (reg.shape[0] if reg is not None else 0)
+        return img.shape[0], (img.shape[2] // ph) * (img.shape[3] // pw) + extra
 
 
 class HeadEngine:
@@ -388,3 +433,27 @@ class HeadEngine:
         out = torch.empty(pooled_bf16.shape[0], t["w"].shape[0], device=pooled_bf16.device, dtype=torch.bfloat16)
         _lib.gemm(pooled_bf16.contiguous(), t["w"], out_bf16=out, bias=t["b"])
         return out
+
+
+def fused_mean_pooled_features(owner: nn.Module, img: torch.Tensor, pool_tokens: Optional[int] = None) -> torch.Tensor:
+    """Shared body of the SimpleViT-family fused forwards (reference simple_vit.py:110-117 and its variants):
+    patch embedding (+ register tokens) -> encoder blocks -> final LayerNorm if the Transformer has one -> mean over
+    the first `pool_tokens` tokens of every image (all tokens by default).  Returns fp32 [B, D]; must run inside
+    on_device(img)."""
+    if getattr(owner, "_patch_engine", None) is None:
+        owner._patch_engine = PatchEmbedEngine(owner)
+    eng = owner.transformer.engine()
+    B, N = owner._patch_engine.geometry(img)
+    primed = ln_mode() == "fold"
+    ws = eng.workspace(B * N, img.device) if primed else None
+    x, B, N = owner._patch_engine.run(img, xb=ws["xn"] if primed else None, stats=ws["stats_in"] if primed else None)
+    D = x.shape[1]
+    eng.run_blocks(x, B, N, primed=primed)
+    if eng.has_final_norm():
+        xf = torch.empty_like(x)
+        eng.final_norm(x, out_f32=xf)
+    else:
+        xf = x
+    pm = torch.empty(B, D, device=img.device, dtype=torch.float32)
+    _lib.mean_pool(xf, pm, B, N, D, n_pool=pool_tokens)
+    return pm
