@@ -357,8 +357,10 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, con
 
 using namespace b200;
 
+namespace b200 { void attention_pipe_set_trace(long long* buf); }
 extern "C" void b200vit_debug_set_trace(void* dev_buf) {
   attention_varlen_set_trace(reinterpret_cast<long long*>(dev_buf));
+  attention_pipe_set_trace(reinterpret_cast<long long*>(dev_buf));
 }
 
 extern "C" int b200vit_debug_set(int key, int value) {

@@ -22,10 +22,13 @@
 // Softmax parallelism: ONE warp per SM sub-partition cannot hide its own instruction latencies (measured: 25 % issue
 // utilisation, MUFU 28 % busy, 3.2 us per tile; profiles/r02a).  So a score tile is worked on by 16 warps: warp w owns
 // TMEM lanes 32 (w % 4) ... +31 (hardware rule) = 32 query rows, and the four warps of a row quadrant split the KEY
-// columns in 16-column chunks (part = w / 4).  Row max and row sum are combined through shared memory with one
-// named barrier per quadrant and tile; the O read-out is split the same way (16 of the 64 columns per warp).
+// columns in units of 8 (part = w / 4; 56 / 56 / 48 / 48 columns at N = 197), each share read from TMEM once and kept
+// in registers.  Row max and row sum are combined through shared memory (one named barrier per quadrant and tile).
+// The O read-out belongs to a warpgroup of its own, so that it overlaps the next tile's softmax (r02d timeline: as
+// part of the softmax warps' loop it cost 0.7 of 2.9 us per tile).
 //
-// Roles: warps 0-15 softmax / epilogue, warp 16 TMA producer, warp 17 MMA issuer + TMEM allocator.
+// Roles: warps 0-15 softmax (4 warpgroups = 4 column parts), 16-19 epilogue (one warp per row quadrant),
+//        20 TMA producer, 21 MMA issuer + TMEM allocator, 22-23 idle (they complete the fifth warpgroup).
 #include "common.cuh"
 #include "host_util.h"
 
@@ -37,7 +40,9 @@ constexpr int KV_STAGES = 3;
 constexpr int Q_SLOTS = 3;
 constexpr int Q_TILE_BYTES = 128 * 128;
 constexpr int SM_WARPS = 16;            // softmax warps: 4 row quadrants x 4 column parts
-constexpr int THREADS = (SM_WARPS + 2) * 32;
+constexpr int EPI_WARPS = 4;            // O read-out: one warp per row quadrant
+constexpr int THREADS = (SM_WARPS + EPI_WARPS + 4) * 32;
+constexpr int SUM_SLOTS = 4;            // ring of row-sum hand-over buffers (softmax -> epilogue warps)
 constexpr int MAX_KP = 224;  // 2 * KP + 64 <= 512 TMEM columns
 }  // namespace ap
 
@@ -52,6 +57,7 @@ struct AttnPipeParams {
   float scale_log2e;
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;
+  long long* trace;  // TRACE instantiation only: [tile][16] %globaltimer stamps of CTA 0 (tools/attn_pipe_trace.py)
 };
 
 // max of three (one FMNMX3 on sm_100 instead of two FMNMX)
@@ -61,10 +67,14 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return r;
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(ap::THREADS, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const AttnPipeParams p) {
   using namespace ap;
+  auto stamp = [&](int j, int slot) {
+    if (TRACE && blockIdx.x == 0 && j < 64) p.trace[j * 16 + slot] = (long long)globaltimer_ns();
+  };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_stage_bytes = 2 * p.kv_bytes;
@@ -78,13 +88,14 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* p_ready = s_full + 2;            // [2]
   uint64_t* o_full = p_ready + 2;            // [1]
   uint64_t* o_free = o_full + 1;             // [1]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* sum_ready = o_free + 1;          // [SUM_SLOTS]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sum_ready + SUM_SLOTS);
   float* pmax = reinterpret_cast<float*>(tmem_base_smem + 4);  // [2 tile parities][4 parts][128 rows]
-  float* psum = pmax + 2 * 4 * 128;                            // [2][4][128]
+  float* psum = pmax + 2 * 4 * 128;                            // [SUM_SLOTS][4][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int TMA_WARP = SM_WARPS, MMA_WARP = SM_WARPS + 1;
+  constexpr int TMA_WARP = SM_WARPS + EPI_WARPS, MMA_WARP = TMA_WARP + 1;
 
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -102,7 +113,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_init(&p_ready[r], SM_WARPS);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_free, SM_WARPS);
+    mbar_init(o_free, EPI_WARPS);
+    for (int r = 0; r < SUM_SLOTS; ++r) mbar_init(&sum_ready[r], SM_WARPS);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -156,6 +168,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (t == 0) mbar_wait(&kv_full[s], (i / KV_STAGES) & 1);
         mbar_wait(&q_full[qs], (j / Q_SLOTS) & 1);
         tc_fence_after();
+        stamp(j, 0);  // S(j): operands present, issue begins
         const uint32_t sk = smem_u32(smem + s * kv_stage_bytes);
         const uint64_t adesc = make_smem_desc_sw128(smem_u32(q_smem + qs * Q_TILE_BYTES), 16, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(sk, 16, 1024);
@@ -164,14 +177,17 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int k = 0; k < DH / 16; ++k) umma_ss(d_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
         umma_commit(&s_full[j & 1]);
         umma_commit(&q_empty[qs]);
+        stamp(j, 1);  // S(j) issued
       };
       // O(j) = P_j V  (A = P from TMEM, B = V as MN-major smem operand: 16 keys = two 8-row groups = 2048 B)
       auto issue_pv = [&](int j) {
         const int i = j / p.nq, t = j - i * p.nq;
         const int s = i % KV_STAGES;
         mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        stamp(j, 2);  // PV(j): P ready seen
         if (j > 0) mbar_wait(o_free, (j - 1) & 1);
         tc_fence_after();
+        stamp(j, 3);  // PV(j): O slot free, issue begins
         const uint32_t sv = smem_u32(smem + s * kv_stage_bytes) + p.kv_bytes;
         const uint32_t a_p = tmem_base + (j & 1) * p.KP;
         for (int k = 0; k < ksteps; ++k) {
@@ -180,6 +196,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         umma_commit(o_full);
         if (t == p.nq - 1) umma_commit(&kv_empty[s]);  // every MMA reading this K/V stage has been issued
+        stamp(j, 4);  // PV(j) issued
       };
       if (n_tiles > 0) issue_s(0);
       if (n_tiles > 1) issue_s(1);
@@ -188,140 +205,160 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (j + 2 < n_tiles) issue_s(j + 2);  // right behind PV(j): overwrites the P it has just consumed (in-order)
       }
     }
-  } else {
-    // ---------------------------------------------------------------- softmax / epilogue warps
-    const int quad = warp & 3;   // TMEM lane quadrant = 32 query rows
-    const int part = warp >> 2;  // which share of the key columns (and of the 64 output columns)
+  } else if (warp >= SM_WARPS && warp < SM_WARPS + EPI_WARPS) {
+    // ---------------------------------------------------------------- epilogue warps: O(j) / rowsum -> bf16 -> out
+    const int quad = warp & 3;
     const int r_in_tile = quad * 32 + lane;
-    const float c = p.scale_log2e;
-    const int nch = p.KP >> 4;  // 16-column chunks, dealt to the four parts as evenly as possible
-    // (the extra chunks go to the LAST parts: a warp's 4th chunk, which is re-read from TMEM instead of being kept in
-    //  registers, then always lies in the upper half of the score columns, which P never overwrites -- see below)
-    const int extra_from = 4 - (nch & 3);
-    const int ch0 = part * (nch >> 2) + max(part - extra_from, 0);
-    const int ch1 = ch0 + (nch >> 2) + (part >= extra_from ? 1 : 0);
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    auto quad_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory"); };
-
-    // O(jj)[:, 16 part .. +16] / rowsum -> bf16 -> out[b, row, h*64 + 16 part ...]
-    auto epilogue = [&](int jj, bool active) {
-      const int i = jj / p.nq, t = jj - i * p.nq;
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + O_COL;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int i = j / p.nq, t = j - i * p.nq;
       const int u = blockIdx.x + i * gridDim.x;
       const int h = u % p.H, b = u / p.H;
       const int qrow = t * 128 + r_in_tile;
-      mbar_wait(o_full, jj & 1);
+      const bool active = t * 128 + quad * 32 < p.N;
+      mbar_wait(&sum_ready[j % SUM_SLOTS], (j / SUM_SLOTS) & 1);  // the 16 partial row sums of this tile are written
+      const float* ps = psum + (j % SUM_SLOTS) * 512 + r_in_tile;
+      const float inv = 1.0f / ((ps[0] + ps[128]) + (ps[256] + ps[384]));
+      mbar_wait(o_full, j & 1);
       tc_fence_after();
-      uint32_t r[16];
+      if (lane == 0 && quad == 0) stamp(j, 12);  // O(j) seen
+      uint32_t r0[32], r1[32];
       if (active) {
-        tmem_ld_32x32b_x16(tmem_base + lane_off + O_COL + part * 16, r);
+        tmem_ld_32x32b_x32(t_o, r0);
+        tmem_ld_32x32b_x32(t_o + 32, r1);
         tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
       if (active && qrow < p.N) {
-        const float* ps = psum + (jj & 1) * 512 + r_in_tile;  // the quadrant barrier of the next tile ordered these
-        const float inv = 1.0f / ((ps[0] + ps[128]) + (ps[256] + ps[384]));
-        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * DH + part * 16);
+        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * DH);
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          op[q] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv),
-                             pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv),
-                             pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv),
-                             pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv));
+        for (int q = 0; q < 4; ++q)
+          op[q] = make_uint4(pack_bf16x2(__uint_as_float(r0[8 * q]) * inv, __uint_as_float(r0[8 * q + 1]) * inv),
+                             pack_bf16x2(__uint_as_float(r0[8 * q + 2]) * inv, __uint_as_float(r0[8 * q + 3]) * inv),
+                             pack_bf16x2(__uint_as_float(r0[8 * q + 4]) * inv, __uint_as_float(r0[8 * q + 5]) * inv),
+                             pack_bf16x2(__uint_as_float(r0[8 * q + 6]) * inv, __uint_as_float(r0[8 * q + 7]) * inv));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          op[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(r1[8 * q]) * inv, __uint_as_float(r1[8 * q + 1]) * inv),
+                                 pack_bf16x2(__uint_as_float(r1[8 * q + 2]) * inv, __uint_as_float(r1[8 * q + 3]) * inv),
+                                 pack_bf16x2(__uint_as_float(r1[8 * q + 4]) * inv, __uint_as_float(r1[8 * q + 5]) * inv),
+                                 pack_bf16x2(__uint_as_float(r1[8 * q + 6]) * inv, __uint_as_float(r1[8 * q + 7]) * inv));
       }
-    };
+      if (lane == 0 && quad == 0) stamp(j, 13);  // epilogue(j) done
+    }
+  } else if (warp < SM_WARPS) {
+    // ---------------------------------------------------------------- softmax warps
+    const int quad = warp & 3;   // TMEM lane quadrant = 32 query rows
+    const int part = warp >> 2;  // which share of the key columns
+    const int r_in_tile = quad * 32 + lane;
+    const float c = p.scale_log2e;
+    // key columns in units of 8, dealt to the four parts as evenly as possible: [u0, u1) units = [c_lo, c_hi) columns
+    const int nun = p.KP >> 3;
+    const int u0 = part * (nun >> 2) + min(part, nun & 3);
+    const int u1 = u0 + (nun >> 2) + (part < (nun & 3) ? 1 : 0);
+    const int c_lo = u0 * 8;
+    const int my_units = u1 - u0;        // <= 7 (KP <= 224): three 16-column loads + one optional 8-column load
+    const int n16 = my_units >> 1;       // 16-column groups held in sv[0 .. 2]
+    const bool odd8 = (my_units & 1) != 0;  // trailing 8-column group held in s8
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    auto quad_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory"); };
 
-    bool active_prev = false;
     for (int j = 0; j < n_tiles; ++j) {
       const int t = j % p.nq;
       // quadrants whose 32 query rows all lie beyond N skip the arithmetic but keep every barrier in lockstep
       const bool active = t * 128 + quad * 32 < p.N;
       const uint32_t t_lane = tmem_base + lane_off + (j & 1) * p.KP;
       float* my_max = pmax + (j & 1) * 512 + part * 128 + r_in_tile;
-      float* my_sum = psum + (j & 1) * 512 + part * 128 + r_in_tile;
+      float* my_sum = psum + (j % SUM_SLOTS) * 512 + part * 128 + r_in_tile;
+      if (warp == 0 && lane == 0) stamp(j, 8);   // softmax(j): waiting for S
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // The warp's share of the score row is read from TMEM ONCE and kept in registers (3 chunks x 16 fp32).  That is
-      // a correctness matter: P is written over S (columns [8 ch, 8 ch + 8) for chunk ch), i.e. into columns other
-      // warps of the quadrant own -- the quadrant barrier below, passed only after every warp's loads have completed,
-      // makes that safe.  A 4th chunk (KP = 208 / 224 only) is re-read after the barrier instead: it sits at columns
-      // >= 144, beyond the [0, KP/2) range P occupies, so nobody overwrites it.
+      if (warp == 0 && lane == 0) stamp(j, 9);   // S(j) seen
+      // The warp's share of the score row is read from TMEM ONCE and kept in registers (<= 56 fp32).  That is a
+      // correctness matter too: P is written over S (4 packed columns per 8 score columns, at column c/2), i.e. into
+      // columns other warps of the quadrant own -- the quadrant barrier below, passed only after every warp's loads
+      // have completed, makes that safe.
       uint32_t sv[3][16];
-      const int my_n = ch1 - ch0;
-      const bool tail = my_n == 4;
-      const int tail_c0 = (ch0 + 3) * 16;
-      // key columns >= N (zero-filled K rows) become -inf right after the load: max ignores them, exp2 gives 0
-      auto mask16 = [&](uint32_t (&r)[16], int c0) {
-        if (c0 + 16 > p.N) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (c0 + q >= p.N) r[q] = 0xff800000u;
-        }
-      };
-      auto max16 = [&](const uint32_t (&r)[16], float& m0, float& m1) {
-#pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-          m0 = max3(m0, __uint_as_float(r[q]), __uint_as_float(r[q + 1]));
-          m1 = max3(m1, __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
-        }
-      };
+      uint32_t s8[8];
+      float sum = 0.f;
       if (active) {
-        // ---------------- row max over this warp's columns
-        float m0 = -INFINITY, m1 = -INFINITY;
-        if (tail) {  // the 4th chunk first, through the registers of chunk 0
-          tmem_ld_32x32b_x16(t_lane + tail_c0, sv[0]);
-          tmem_ld_wait();
-          mask16(sv[0], tail_c0);
-          max16(sv[0], m0, m1);
-        }
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          if (k < my_n) tmem_ld_32x32b_x16(t_lane + (ch0 + k) * 16, sv[k]);
+          if (k < n16) tmem_ld_32x32b_x16(t_lane + c_lo + k * 16, sv[k]);
+        if (odd8) tmem_ld_32x32b_x8(t_lane + c_lo + n16 * 16, s8);
         tmem_ld_wait();
+        // key columns >= N (zero-filled K rows) become -inf: max ignores them, exp2 gives 0
+        float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          if (k < my_n) {
-            mask16(sv[k], (ch0 + k) * 16);
-            max16(sv[k], m0, m1);
+          if (k < n16) {
+            const int c0 = c_lo + k * 16;
+            if (c0 + 16 > p.N) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (c0 + q >= p.N) sv[k][q] = 0xff800000u;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              m0 = max3(m0, __uint_as_float(sv[k][q]), __uint_as_float(sv[k][q + 1]));
+              m1 = max3(m1, __uint_as_float(sv[k][q + 2]), __uint_as_float(sv[k][q + 3]));
+            }
+          }
+        }
+        if (odd8) {
+          const int c0 = c_lo + n16 * 16;
+          if (c0 + 8 > p.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (c0 + q >= p.N) s8[q] = 0xff800000u;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; q += 4) {
+            m0 = max3(m0, __uint_as_float(s8[q]), __uint_as_float(s8[q + 1]));
+            m1 = max3(m1, __uint_as_float(s8[q + 2]), __uint_as_float(s8[q + 3]));
           }
         }
         *my_max = fmaxf(m0, m1);
       }
       tc_fence_before();
-      quad_barrier();  // partial maxima (and the previous tile's partial sums) visible; every S load has completed
+      quad_barrier();  // partial maxima visible; every S load of the quadrant has completed
       tc_fence_after();
-      float sum = 0.f;
+      if (warp == 0 && lane == 0) stamp(j, 10);  // past the quadrant barrier
       if (active) {
         const float* pm = pmax + (j & 1) * 512 + r_in_tile;
         const float mc = fmaxf(fmaxf(pm[0], pm[128]), fmaxf(pm[256], pm[384])) * c;
         // ---------------- p = exp2(s*c - max*c), partial row sum, P (bf16 pairs) -> TMEM over S
         const f32x2 c2v = f2_make(c, c), nmc2v = f2_make(-mc, -mc);
         f32x2 acc0 = f2_make(0.f, 0.f), acc1 = f2_make(0.f, 0.f);
-        auto exp16 = [&](const uint32_t (&r)[16], int c0) {
-          uint32_t pk[8];
+#define AP_EXP4(R, Q, PK, I)                                                                               \
+  {                                                                                                        \
+    float x0, x1, x2, x3;                                                                                  \
+    f2_get(f2_fma(f2_make(__uint_as_float(R[Q]), __uint_as_float(R[Q + 1])), c2v, nmc2v), x0, x1);         \
+    f2_get(f2_fma(f2_make(__uint_as_float(R[Q + 2]), __uint_as_float(R[Q + 3])), c2v, nmc2v), x2, x3);     \
+    const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);                \
+    acc0 = f2_add(acc0, f2_make(e0, e1));                                                                  \
+    acc1 = f2_add(acc1, f2_make(e2, e3));                                                                  \
+    PK[I] = pack_bf16x2(e0, e1);                                                                           \
+    PK[I + 1] = pack_bf16x2(e2, e3);                                                                       \
+  }
 #pragma unroll
-          for (int q = 0; q < 16; q += 4) {
-            float x0, x1, x2, x3;
-            f2_get(f2_fma(f2_make(__uint_as_float(r[q]), __uint_as_float(r[q + 1])), c2v, nmc2v), x0, x1);
-            f2_get(f2_fma(f2_make(__uint_as_float(r[q + 2]), __uint_as_float(r[q + 3])), c2v, nmc2v), x2, x3);
-            const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);
-            acc0 = f2_add(acc0, f2_make(e0, e1));
-            acc1 = f2_add(acc1, f2_make(e2, e3));
-            pk[q >> 1] = pack_bf16x2(e0, e1);
-            pk[(q >> 1) + 1] = pack_bf16x2(e2, e3);
+        for (int k = 0; k < 3; ++k) {
+          if (k < n16) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) AP_EXP4(sv[k], q, pk, q >> 1)
+            tmem_st_32x32b_x8(t_lane + ((c_lo + k * 16) >> 1), pk);
           }
-          tmem_st_32x32b_x8(t_lane + (c0 >> 1), pk);
-        };
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < my_n) exp16(sv[k], (ch0 + k) * 16);
-        if (tail) {  // (re-read: columns >= 144 are never overwritten by P)
-          tmem_ld_32x32b_x16(t_lane + tail_c0, sv[0]);
-          tmem_ld_wait();
-          mask16(sv[0], tail_c0);
-          exp16(sv[0], tail_c0);
         }
+        if (odd8) {
+          uint32_t pk4[4];
+          AP_EXP4(s8, 0, pk4, 0)
+          AP_EXP4(s8, 4, pk4, 2)
+          tmem_st_32x32b_x4(t_lane + ((c_lo + n16 * 16) >> 1), pk4);
+        }
+#undef AP_EXP4
         float s0, s1, s2, s3;
         f2_get(acc0, s0, s1);
         f2_get(acc1, s2, s3);
@@ -331,15 +368,11 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       *my_sum = sum;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
-
-      // O of the PREVIOUS tile: its PV ran while this tile's softmax was computed
-      if (j > 0) epilogue(j - 1, active_prev);
-      active_prev = active;
-    }
-    if (n_tiles > 0) {
-      quad_barrier();  // the last tile's partial sums
-      epilogue(n_tiles - 1, active_prev);
+      if (lane == 0) {
+        mbar_arrive(&p_ready[j & 1]);
+        mbar_arrive(&sum_ready[j % SUM_SLOTS]);
+      }
+      if (warp == 0 && lane == 0) stamp(j, 11);  // P(j) handed over
     }
   }
 
@@ -353,6 +386,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 // eligible: dh = 64, 2 * KP + 64 <= 512
 bool attention_pipe_eligible(int N, int dh) { return dh == ap::DH && (N + 15) / 16 * 16 <= ap::MAX_KP; }
+
+static std::atomic<long long*> g_pipe_trace{nullptr};
+void attention_pipe_set_trace(long long* buf) { g_pipe_trace = buf; }
 
 int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
                           cudaStream_t stream) {
@@ -369,6 +405,7 @@ int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.v_lbo = v_lbo;
   p.v_sbo = v_sbo;
+  p.trace = g_pipe_trace.load();
   B200_CHECK_ARG(p.kv_bytes % 1024 == 0, "attention: K/V slab of %d bytes is not 1024-byte aligned", p.kv_bytes);
 
   CUtensorMap tmQ, tmKV;
@@ -385,12 +422,19 @@ int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float
     if (rc) return rc;
   }
   const size_t smem_bytes = (size_t)KV_STAGES * 2 * p.kv_bytes + (size_t)Q_SLOTS * Q_TILE_BYTES +
-                            (2 * KV_STAGES + 2 * Q_SLOTS + 6) * 8 + 16 + 2 * 2 * 4 * 128 * sizeof(float) + 1024;
+                            (2 * KV_STAGES + 2 * Q_SLOTS + 6 + SUM_SLOTS) * 8 + 16 +
+                            (2 + SUM_SLOTS) * 4 * 128 * sizeof(float) + 1024;
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
-  B200_ENSURE_SMEM(attention_pipe_kernel, smem_bytes);
   const int grid = p.units < num_sms() ? p.units : num_sms();
-  B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel, dim3(grid), dim3(THREADS), smem_bytes, stream, /*pdl=*/true,
-                                tmQ, tmKV, p));
+  if (p.trace) {  // timing experiment (test hook): separately compiled instantiation
+    B200_ENSURE_SMEM(attention_pipe_kernel<true>, smem_bytes);
+    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<true>, dim3(grid), dim3(THREADS), smem_bytes, stream, false,
+                                  tmQ, tmKV, p));
+  } else {
+    B200_ENSURE_SMEM(attention_pipe_kernel<false>, smem_bytes);
+    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<false>, dim3(grid), dim3(THREADS), smem_bytes, stream,
+                                  /*pdl=*/true, tmQ, tmKV, p));
+  }
   count_launch();
   return 0;
 }
