@@ -184,11 +184,12 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
 /*
  * TEST HOOKS -- process-global switches for A/B tests and bring-up; NOT part of the re-entrant API above (a value set
  * here changes every later call of every thread).  Production code never calls them.
- *   key 1: b200vit_attention kernel choice: 0 = auto (pipelined kernel for N <= 224), 1 = round-1 kernels only
+ *   key 1: b200vit_attention kernel choice: 0 = auto, 1 = round-1 kernels only, 2 = pipelined kernel wherever N <= 224
  *   key 2 / 3: V (MN-major) descriptor LBO / SBO bytes (bring-up probe)
  *   key 4: GEMM kernel choice: 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies
  *   key 11: varlen attention kernel: 0 = pipelined 64-key blocks (default), 1 = serial 128-key blocks
  *   key 12: fp32-epilogue warps of the CTA-pair GEMM: 0 = auto (4 when K >= 2048, else 8), 4 / 8 = forced
+ *   key 13: pipelined attention: 0 = all softmax exponentials on MUFU (default), 1 = half of them on the FMA pipe
  */
 int b200vit_debug_set(int key, int value);
 /* timing experiment: device buffer of int64[64][16] receiving %globaltimer stamps of CTA 0 of b200vit_attention_varlen */

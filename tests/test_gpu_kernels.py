@@ -219,13 +219,19 @@ def test_gelu_epilogue_accuracy():
                                    # wrap-around of the 3 K/V stages), one-tile units, the 224-key TMEM limit, and 225
                                    # keys = first shape of the round-1 kernel again
                                    (40, 197, 12), (70, 196, 16), (200, 128, 3), (37, 224, 5), (3, 225, 2), (9, 33, 7)])
-def test_attention(B, N, H):
+@pytest.mark.parametrize("kernel", [0, 2])      # test hook 1: 0 = default kernels, 2 = pipelined kernel (N <= 224)
+def test_attention(B, N, H, kernel):
     torch.manual_seed(N)
     dh = 64
     I = H * dh
     qkv = torch.randn(B * N, 3 * I, device=DEV).bfloat16()
     out = torch.zeros(B * N, I, device=DEV, dtype=torch.bfloat16)
-    _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+    _lib.lib().b200vit_debug_set(1, kernel)
+    try:
+        _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().b200vit_debug_set(1, 0)
     q, k, v = qkv.float().cpu().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
     ref = (O.softmax_last((q @ k.transpose(-1, -2)) * dh ** -0.5) @ v).permute(0, 2, 1, 3).reshape(B * N, I)
     # bf16 P and bf16 output: rtol 1e-2 / atol 1e-3 per element, allow 0.5 % stragglers
@@ -233,10 +239,10 @@ def test_attention(B, N, H):
     assert (out.float().cpu() - ref).abs().max() < 2e-2
 
 
-@pytest.mark.parametrize("knob,value,B,N", [(1, 1, 3, 197), (1, 1, 40, 128), (1, 1, 2, 50)])
-def test_attention_round1_kernels_agree_with_the_pipelined_one(knob, value, B, N):
-    """b200vit_debug_set(1, 1) routes N <= 224 to the round-1 kernels (the ones N > 224 always uses): both
-    implementations must produce the same attention."""
+@pytest.mark.parametrize("knob,value,B,N", [(1, 2, 3, 197), (1, 2, 40, 128), (1, 2, 2, 50), (13, 1, 3, 197)])
+def test_attention_kernel_variants_agree(knob, value, B, N):
+    """b200vit_debug_set(1, 2) routes N <= 224 to the software-pipelined kernel, (13, 1) puts half of its
+    exponentials on the FMA pipe: every implementation must produce the same attention."""
     L = _lib.lib()
     torch.manual_seed(7)
     H, dh = 4, 64
@@ -245,11 +251,14 @@ def test_attention_round1_kernels_agree_with_the_pipelined_one(knob, value, B, N
     _lib.attention(qkv, ref_out, B, N, H, dh, dh ** -0.5)
     out = torch.zeros_like(ref_out)
     L.b200vit_debug_set(knob, value)
+    if knob == 13:
+        L.b200vit_debug_set(1, 2)
     try:
         _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
         torch.cuda.synchronize()
     finally:
         L.b200vit_debug_set(knob, 0)
+        L.b200vit_debug_set(1, 0)
     assert within(out, ref_out.float().cpu(), rtol=2e-2, atol=2e-3) > 0.999
 
 
@@ -258,6 +267,7 @@ def test_attention_is_deterministic_and_batch_invariant():
     lands in the batch and on repeated launches."""
     torch.manual_seed(11)
     B, N, H, dh = 64, 197, 12, 64
+    _lib.lib().b200vit_debug_set(1, 2)          # the persistent pipelined kernel (test hook), restored below
     qkv = torch.randn(B * N, 3 * H * dh, device=DEV).bfloat16()
     out = torch.zeros(B * N, H * dh, device=DEV, dtype=torch.bfloat16)
     out2 = torch.zeros_like(out)
@@ -267,6 +277,8 @@ def test_attention_is_deterministic_and_batch_invariant():
     sub = qkv[5 * N: 9 * N].contiguous()
     out3 = torch.zeros(4 * N, H * dh, device=DEV, dtype=torch.bfloat16)
     _lib.attention(sub, out3, 4, N, H, dh, dh ** -0.5)
+    torch.cuda.synchronize()
+    _lib.lib().b200vit_debug_set(1, 0)
     assert torch.equal(out3, out[5 * N: 9 * N])
 
 

@@ -14,6 +14,7 @@ L.b200vit_debug_set_trace.argtypes = [ctypes.c_void_p]
 B, N, H = 512, 197, 12
 qkv = (torch.randn(B * N, 3 * H * 64, device="cuda") * 0.5).bfloat16()
 o = torch.zeros(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
+L.b200vit_debug_set(1, 2)
 for _ in range(2):
     _lib.attention(qkv, o, B, N, H, 64, 0.125)
 tr = torch.zeros(64 * 16, dtype=torch.int64, device="cuda")
@@ -23,8 +24,9 @@ torch.cuda.synchronize()
 L.b200vit_debug_set_trace(None)
 t = tr.cpu().view(64, 16)
 t0 = int(t[t > 0].min())
-names = {0: "S.ops", 1: "S.iss", 2: "PV.p", 3: "PV.o", 4: "PV.iss", 8: "sm.wait", 9: "sm.S", 10: "sm.bar", 11: "sm.P",
-         12: "ep.O", 13: "ep.done"}
-print("tile " + " ".join(f"{names[k]:>8}" for k in sorted(names)))
-for j in range(24, 40):
-    print(f"{j:4d} " + " ".join(f"{(int(t[j, k]) - t0) / 1e3:8.2f}" if t[j, k] > 0 else "       -" for k in sorted(names)))
+names = {0: "S.ops", 1: "S.iss", 2: "PV.p", 3: "PV.o", 4: "PV.iss", 8: "w0.wait", 9: "w0.S", 5: "w0.ld", 10: "w0.bar",
+         6: "w0.exp", 11: "w0.P", 14: "w13.ld", 15: "w13.bar", 7: "w13.P", 12: "ep.O", 13: "ep.done"}
+order = [0, 1, 8, 9, 5, 10, 6, 11, 14, 15, 7, 2, 3, 4, 12, 13]
+print("tile " + " ".join(f"{names[k]:>8}" for k in order))
+for j in range(28, 40):
+    print(f"{j:4d} " + " ".join(f"{(int(t[j, k]) - t0) / 1e3:8.2f}" if t[j, k] > 0 else "       -" for k in order))

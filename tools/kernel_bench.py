@@ -73,8 +73,8 @@ def main():
 
     # ---- attention
     attn_bytes = (qkv.numel() + o.numel()) * 2
-    for mode, tag in ((0, "pipe"), (1, "round1")):
-        if N > 224 and mode == 0:
+    for mode, tag in ((2, "pipe"), (1, "round1")):
+        if N > 224 and mode == 2:
             continue
         L.b200vit_debug_set(1, mode)
         add(f"attention_{tag}", lambda: _lib.attention(qkv, o, B, N, H, 64, 0.125), flops=4.0 * B * H * N * N * 64,

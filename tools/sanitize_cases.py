@@ -34,7 +34,7 @@ if "gemm" in which:
     print("gemm cases done")
 
 if "attention" in which:
-    for mode, (B, N, H) in ((0, (3, 197, 2)), (0, (160, 64, 2)), (1, (2, 197, 2)), (0, (1, 300, 1)), (0, (2, 50, 3))):
+    for mode, (B, N, H) in ((2, (3, 197, 2)), (2, (160, 64, 2)), (1, (2, 197, 2)), (0, (1, 300, 1)), (0, (2, 50, 3))):
         L.b200vit_debug_set(1, mode)
         qkv = torch.randn(B * N, 3 * H * 64, device=dev).bfloat16()
         o = torch.zeros(B * N, H * 64, device=dev, dtype=torch.bfloat16)

@@ -7,13 +7,14 @@ fails, a RuntimeError is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libb200vit.so"
+LIB_PATH = Path(os.environ["B200VIT_LIB"]).resolve() if os.environ.get("B200VIT_LIB") else _PKG / "lib" / "libb200vit.so"
 
 EPI_BIAS = 1
 EPI_GELU = 2

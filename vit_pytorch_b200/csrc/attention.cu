@@ -332,7 +332,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // test hooks (b200vit_debug_set): process-global, NOT part of the re-entrant API
-static std::atomic<int> g_attn_mode{0};   // 0 auto (pipelined kernel when N <= 224), 1 force the round-1 kernels below
+// 0 auto, 1 force the kernels below, 2 force the pipelined kernel (attention_pipe.cu) wherever N <= 224.  Auto is
+// currently the kernels below: at ViT-B/16 batch 512 they need 221 us per layer, the pipelined one 235 us
+// (profiles/r02_attention.md has the timelines and the reasons).
+static std::atomic<int> g_attn_mode{0};
 static std::atomic<int> g_attn_v_lbo{1024};  // V descriptor leading-dim byte offset (bring-up probe)
 static std::atomic<int> g_attn_v_sbo{1024};  // V descriptor stride-dim byte offset
 
@@ -357,7 +360,10 @@ static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, con
 
 using namespace b200;
 
-namespace b200 { void attention_pipe_set_trace(long long* buf); }
+namespace b200 {
+void attention_pipe_set_trace(long long* buf);
+void attention_pipe_set_emul(int v);
+}
 extern "C" void b200vit_debug_set_trace(void* dev_buf) {
   attention_varlen_set_trace(reinterpret_cast<long long*>(dev_buf));
   attention_pipe_set_trace(reinterpret_cast<long long*>(dev_buf));
@@ -370,6 +376,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 3: g_attn_v_sbo = value; return 0;
     case 4: gemm_force_version(value); return 0;
     case 12: gemm2_force_epilogue_warps(value); return 0;
+    case 13: attention_pipe_set_emul(value); return 0;
     case 11: attention_varlen_set_mode(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
@@ -383,7 +390,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "attention: pointers must be 16-byte aligned");
   const int mode = g_attn_mode.load();
-  if (mode != 1 && attention_pipe_eligible(N, dh))
+  if (mode == 2 && attention_pipe_eligible(N, dh))
     return launch_attention_pipe(qkv, out, B, N, H, scale, (unsigned)g_attn_v_lbo.load(), (unsigned)g_attn_v_sbo.load(),
                                  reinterpret_cast<cudaStream_t>(stream));
   AttnParams p{};

@@ -51,6 +51,7 @@ struct AttnPipeParams {
   int KP;           // keys padded to a multiple of 16
   int kv_rows;      // rows of the K / V TMA box (KP rounded up to 8)
   int kv_bytes;     // bytes of one K (or V) slab = kv_rows * 128, multiple of 1024
+  int kv_stages;    // K/V ring depth: 3, or 2 when three stages do not fit shared memory (KP = 224)
   int nq;           // query tiles per unit = ceil(N / 128)
   int units;        // B * H
   int I;            // H * dh
@@ -67,7 +68,9 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return r;
 }
 
-template <bool TRACE>
+// EMUL: every second pair of exponentials is evaluated on the FMA pipe (exp2_emul2) instead of MUFU -- the exponential
+// phase is MUFU-throughput bound (r02j timeline: 1.3 us per tile against 0.85 us of MUFU issue).
+template <bool TRACE, bool EMUL>
 __global__ void __launch_bounds__(ap::THREADS, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const AttnPipeParams p) {
@@ -78,7 +81,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_stage_bytes = 2 * p.kv_bytes;
-  uint8_t* q_smem = smem + KV_STAGES * kv_stage_bytes;
+  uint8_t* q_smem = smem + p.kv_stages * kv_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_smem + Q_SLOTS * Q_TILE_BYTES);
   uint64_t* kv_full = bars;                  // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;  // [KV_STAGES]
@@ -141,8 +144,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int i = 0; i < n_units; ++i) {
         const int u = blockIdx.x + i * gridDim.x;
         const int h = u % p.H, b = u / p.H;
-        const int s = i % KV_STAGES;
-        mbar_wait(&kv_empty[s], ((i / KV_STAGES) & 1) ^ 1);
+        const int s = i % p.kv_stages;
+        mbar_wait(&kv_empty[s], ((i / p.kv_stages) & 1) ^ 1);
         uint8_t* sk = smem + s * kv_stage_bytes;
         mbar_arrive_expect_tx(&kv_full[s], 2 * p.kv_bytes);
         tma_load_3d(sk, &tmKV, &kv_full[s], p.I + h * DH, 0, b);
@@ -164,8 +167,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // S(j) = Q_j K^T into score region j & 1
       auto issue_s = [&](int j) {
         const int i = j / p.nq, t = j - i * p.nq;
-        const int s = i % KV_STAGES, qs = j % Q_SLOTS;
-        if (t == 0) mbar_wait(&kv_full[s], (i / KV_STAGES) & 1);
+        const int s = i % p.kv_stages, qs = j % Q_SLOTS;
+        if (t == 0) mbar_wait(&kv_full[s], (i / p.kv_stages) & 1);
         mbar_wait(&q_full[qs], (j / Q_SLOTS) & 1);
         tc_fence_after();
         stamp(j, 0);  // S(j): operands present, issue begins
@@ -182,7 +185,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // O(j) = P_j V  (A = P from TMEM, B = V as MN-major smem operand: 16 keys = two 8-row groups = 2048 B)
       auto issue_pv = [&](int j) {
         const int i = j / p.nq, t = j - i * p.nq;
-        const int s = i % KV_STAGES;
+        const int s = i % p.kv_stages;
         mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
         stamp(j, 2);  // PV(j): P ready seen
         if (j > 0) mbar_wait(o_free, (j - 1) & 1);
@@ -258,43 +261,60 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int nun = p.KP >> 3;
     const int u0 = part * (nun >> 2) + min(part, nun & 3);
     const int u1 = u0 + (nun >> 2) + (part < (nun & 3) ? 1 : 0);
-    const int c_lo = u0 * 8;
-    const int my_units = u1 - u0;        // <= 7 (KP <= 224): three 16-column loads + one optional 8-column load
-    const int n16 = my_units >> 1;       // 16-column groups held in sv[0 .. 2]
-    const bool odd8 = (my_units & 1) != 0;  // trailing 8-column group held in s8
+    // The share [8 u0, 8 u1) is read as naturally aligned groups (tcgen05.ld column addresses are kept multiples of
+    // the group width): an 8-column group in front if the share starts at an odd unit, then up to three 16-column
+    // groups, then an 8-column group at the end if one unit is left.  (With KP a multiple of 16 a share never needs
+    // both 8-column groups, so one register array serves either.)
+    const bool lead8 = (u0 & 1) != 0 && u1 > u0;
+    const int c16 = (u0 + (lead8 ? 1 : 0)) * 8;            // first 16-column group
+    const int n16 = (u1 - u0 - (lead8 ? 1 : 0)) >> 1;      // <= 3
+    const bool trail8 = ((u1 - u0 - (lead8 ? 1 : 0)) & 1) != 0;
+    const bool has8 = lead8 || trail8;
+    const int c8 = lead8 ? u0 * 8 : c16 + n16 * 16;        // the 8-column group, if any
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     auto quad_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory"); };
 
+    // The warp's share of the score row is read from TMEM ONCE and kept in registers (<= 56 fp32).  That is a
+    // correctness matter too: P is written over S (4 packed columns per 8 score columns, at column c/2), i.e. into
+    // columns other warps of the quadrant own -- the quadrant barrier, passed only after every warp's loads have
+    // completed, makes that safe.
+    uint32_t sv[3][16];
+    uint32_t s8[8];
+    // wait for S(j) and issue (not await) the TMEM loads of this warp's share
+    auto fetch_scores = [&](int j) {
+      if (warp == 0 && lane == 0) stamp(j, 8);   // softmax(j): waiting for S
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) stamp(j, 9);   // S(j) seen
+      if ((j % p.nq) * 128 + quad * 32 < p.N) {
+        const uint32_t tl = tmem_base + lane_off + (j & 1) * p.KP;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < n16) tmem_ld_32x32b_x16(tl + c16 + k * 16, sv[k]);
+        if (has8) tmem_ld_32x32b_x8(tl + c8, s8);
+      }
+    };
     for (int j = 0; j < n_tiles; ++j) {
+      fetch_scores(j);
       const int t = j % p.nq;
       // quadrants whose 32 query rows all lie beyond N skip the arithmetic but keep every barrier in lockstep
       const bool active = t * 128 + quad * 32 < p.N;
       const uint32_t t_lane = tmem_base + lane_off + (j & 1) * p.KP;
       float* my_max = pmax + (j & 1) * 512 + part * 128 + r_in_tile;
       float* my_sum = psum + (j % SUM_SLOTS) * 512 + part * 128 + r_in_tile;
-      if (warp == 0 && lane == 0) stamp(j, 8);   // softmax(j): waiting for S
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      if (warp == 0 && lane == 0) stamp(j, 9);   // S(j) seen
-      // The warp's share of the score row is read from TMEM ONCE and kept in registers (<= 56 fp32).  That is a
-      // correctness matter too: P is written over S (4 packed columns per 8 score columns, at column c/2), i.e. into
-      // columns other warps of the quadrant own -- the quadrant barrier below, passed only after every warp's loads
-      // have completed, makes that safe.
-      uint32_t sv[3][16];
-      uint32_t s8[8];
+      // (Issuing the NEXT tile's loads before waiting for this tile's tcgen05.st -- software pipelining across
+      //  tiles -- was measured: 235 -> 321 us per layer, the extra live registers spill under the 80-register cap.)
       float sum = 0.f;
       if (active) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < n16) tmem_ld_32x32b_x16(t_lane + c_lo + k * 16, sv[k]);
-        if (odd8) tmem_ld_32x32b_x8(t_lane + c_lo + n16 * 16, s8);
         tmem_ld_wait();
+        if (lane == 0 && warp == 0) stamp(j, 5);    // warp 0: S in registers
+        if (lane == 0 && warp == 13) stamp(j, 14);  // warp 13 (quadrant 1, part 3): S in registers
         // key columns >= N (zero-filled K rows) become -inf: max ignores them, exp2 gives 0
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           if (k < n16) {
-            const int c0 = c_lo + k * 16;
+            const int c0 = c16 + k * 16;
             if (c0 + 16 > p.N) {
 #pragma unroll
               for (int q = 0; q < 16; ++q)
@@ -307,8 +327,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
           }
         }
-        if (odd8) {
-          const int c0 = c_lo + n16 * 16;
+        if (has8) {
+          const int c0 = c8;
           if (c0 + 8 > p.N) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -326,6 +346,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       quad_barrier();  // partial maxima visible; every S load of the quadrant has completed
       tc_fence_after();
       if (warp == 0 && lane == 0) stamp(j, 10);  // past the quadrant barrier
+      if (warp == 13 && lane == 0) stamp(j, 15);
       if (active) {
         const float* pm = pmax + (j & 1) * 512 + r_in_tile;
         const float mc = fmaxf(fmaxf(pm[0], pm[128]), fmaxf(pm[256], pm[384])) * c;
@@ -335,13 +356,20 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #define AP_EXP4(R, Q, PK, I)                                                                               \
   {                                                                                                        \
     float x0, x1, x2, x3;                                                                                  \
-    f2_get(f2_fma(f2_make(__uint_as_float(R[Q]), __uint_as_float(R[Q + 1])), c2v, nmc2v), x0, x1);         \
-    f2_get(f2_fma(f2_make(__uint_as_float(R[Q + 2]), __uint_as_float(R[Q + 3])), c2v, nmc2v), x2, x3);     \
-    const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);                \
+    f2_get(f2_fma(f2_make(__uint_as_float(R[(Q)]), __uint_as_float(R[(Q) + 1])), c2v, nmc2v), x0, x1);     \
+    f2_get(f2_fma(f2_make(__uint_as_float(R[(Q) + 2]), __uint_as_float(R[(Q) + 3])), c2v, nmc2v), x2, x3); \
+    const float e0 = fast_ex2(x0), e1 = fast_ex2(x1);                                                      \
+    float e2, e3;                                                                                          \
+    if (EMUL) {                                                                                            \
+      exp2_emul2(f2_make(x2, x3), e2, e3);                                                                 \
+    } else {                                                                                               \
+      e2 = fast_ex2(x2);                                                                                   \
+      e3 = fast_ex2(x3);                                                                                   \
+    }                                                                                                      \
     acc0 = f2_add(acc0, f2_make(e0, e1));                                                                  \
     acc1 = f2_add(acc1, f2_make(e2, e3));                                                                  \
-    PK[I] = pack_bf16x2(e0, e1);                                                                           \
-    PK[I + 1] = pack_bf16x2(e2, e3);                                                                       \
+    PK[(I)] = pack_bf16x2(e0, e1);                                                                         \
+    PK[(I) + 1] = pack_bf16x2(e2, e3);                                                                     \
   }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -349,23 +377,24 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             uint32_t pk[8];
 #pragma unroll
             for (int q = 0; q < 16; q += 4) AP_EXP4(sv[k], q, pk, q >> 1)
-            tmem_st_32x32b_x8(t_lane + ((c_lo + k * 16) >> 1), pk);
+            tmem_st_32x32b_x8(t_lane + ((c16 + k * 16) >> 1), pk);
           }
         }
-        if (odd8) {
+        if (has8) {
           uint32_t pk4[4];
           AP_EXP4(s8, 0, pk4, 0)
           AP_EXP4(s8, 4, pk4, 2)
-          tmem_st_32x32b_x4(t_lane + ((c_lo + n16 * 16) >> 1), pk4);
+          tmem_st_32x32b_x4(t_lane + (c8 >> 1), pk4);
         }
 #undef AP_EXP4
         float s0, s1, s2, s3;
         f2_get(acc0, s0, s1);
         f2_get(acc1, s2, s3);
         sum = (s0 + s1) + (s2 + s3);
-        tmem_st_wait();
+        if (lane == 0 && warp == 0) stamp(j, 6);    // warp 0: exponentials computed, P stores issued
       }
       *my_sum = sum;
+      if (active) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -373,6 +402,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_arrive(&sum_ready[j % SUM_SLOTS]);
       }
       if (warp == 0 && lane == 0) stamp(j, 11);  // P(j) handed over
+      if (warp == 13 && lane == 0) stamp(j, 7);
     }
   }
 
@@ -389,6 +419,8 @@ bool attention_pipe_eligible(int N, int dh) { return dh == ap::DH && (N + 15) / 
 
 static std::atomic<long long*> g_pipe_trace{nullptr};
 void attention_pipe_set_trace(long long* buf) { g_pipe_trace = buf; }
+static std::atomic<int> g_pipe_emul{0};  // test hook 13: 0 = all exponentials on MUFU (default), 1 = half on the FMA pipe
+void attention_pipe_set_emul(int v) { g_pipe_emul = v; }
 
 int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
                           cudaStream_t stream) {
@@ -421,18 +453,26 @@ int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float
     int rc = encode_tmap_bf16(&tmKV, qkv, 3, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem_bytes = (size_t)KV_STAGES * 2 * p.kv_bytes + (size_t)Q_SLOTS * Q_TILE_BYTES +
-                            (2 * KV_STAGES + 2 * Q_SLOTS + 6 + SUM_SLOTS) * 8 + 16 +
-                            (2 + SUM_SLOTS) * 4 * 128 * sizeof(float) + 1024;
+  auto smem_for = [&](int stages) {
+    return (size_t)stages * 2 * p.kv_bytes + (size_t)Q_SLOTS * Q_TILE_BYTES +
+           (2 * KV_STAGES + 2 * Q_SLOTS + 6 + SUM_SLOTS) * 8 + 16 + (2 + SUM_SLOTS) * 4 * 128 * sizeof(float) + 1024;
+  };
+  p.kv_stages = smem_for(KV_STAGES) <= 227 * 1024 ? KV_STAGES : KV_STAGES - 1;
+  const size_t smem_bytes = smem_for(p.kv_stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   const int grid = p.units < num_sms() ? p.units : num_sms();
+  const bool emul = g_pipe_emul.load() != 0;
   if (p.trace) {  // timing experiment (test hook): separately compiled instantiation
-    B200_ENSURE_SMEM(attention_pipe_kernel<true>, smem_bytes);
-    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<true>, dim3(grid), dim3(THREADS), smem_bytes, stream, false,
-                                  tmQ, tmKV, p));
+    B200_ENSURE_SMEM((attention_pipe_kernel<true, true>), smem_bytes);
+    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<true, true>, dim3(grid), dim3(THREADS), smem_bytes, stream,
+                                  false, tmQ, tmKV, p));
+  } else if (emul) {
+    B200_ENSURE_SMEM((attention_pipe_kernel<false, true>), smem_bytes);
+    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<false, true>, dim3(grid), dim3(THREADS), smem_bytes, stream,
+                                  /*pdl=*/true, tmQ, tmKV, p));
   } else {
-    B200_ENSURE_SMEM(attention_pipe_kernel<false>, smem_bytes);
-    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<false>, dim3(grid), dim3(THREADS), smem_bytes, stream,
+    B200_ENSURE_SMEM((attention_pipe_kernel<false, false>), smem_bytes);
+    B200_CHECK_CUDA(launch_kernel(attention_pipe_kernel<false, false>, dim3(grid), dim3(THREADS), smem_bytes, stream,
                                   /*pdl=*/true, tmQ, tmKV, p));
   }
   count_launch();
