@@ -35,7 +35,8 @@ extern "C" {
 #define B200VIT_EPI_RESIDUAL 4  /* + resid[m, n] (fp32); resid may alias out_f32 (in-place residual stream) */
 #define B200VIT_EPI_LNFOLD 8    /* A is the un-normalised bf16 row, W carries gamma: y = rstd_m*(acc - mu_m*s_n) + bias_n */
 #define B200VIT_EPI_STATS 16    /* write per-row partial (sum, sum^2) of the bf16-rounded result into stats_out */
-#define B200VIT_EPI_HEADNORM 32 /* internal to b200vit_gemm_headnorm_bf16: RMS-normalise leading 64-wide heads */
+#define B200VIT_EPI_HEADNORM 32 /* internal to b200vit_gemm_headnorm_bf16: normalise leading 64-wide heads */
+#define B200VIT_EPI_HEADLN 64   /* b200vit_gemm_headnorm_bf16: per-head LayerNorm (no bias) instead of the RMS norm */
 
 const char* b200vit_last_error(void);
 int b200vit_version(void);
@@ -140,13 +141,15 @@ int b200vit_qk_rmsnorm(void* qkv, const float* gamma_qk, int T, int H, int dh, v
  *   out[M, N] bf16 = epilogue(A W^T)   with flags in {EPI_BIAS, EPI_LNFOLD} exactly as b200vit_gemm_bf16, then the first
  *   norm_heads heads (dh = 64 columns each, from column 0) of every row are replaced by
  *   v / max(||v||, 1e-12) * sqrt(dh) * head_gamma[h, d]   (norm computed on the bf16-rounded projection, like the
- *   reference's bf16 module).  Large problems run the RMSNorm inside the CTA-pair GEMM epilogue (one warp owns one
- *   head of 32 rows); small ones run b200vit_gemm_bf16 + b200vit_rmsnorm_heads.
+ *   reference's bf16 module).  Large problems run the norm inside the CTA-pair GEMM epilogue (one warp owns one
+ *   head of 32 rows); small ones run b200vit_gemm_bf16 + b200vit_rmsnorm_heads / b200vit_layernorm_heads.
+ *   flags | EPI_HEADLN: the heads get nn.LayerNorm(dh, bias=False) instead -- (v - mean) * rsqrt(var + head_eps) *
+ *   head_gamma[h, d] -- the q / k norm of the nested-tensor NaViT (na_vit_nested_tensor.py:61-62,101-102).
  */
 int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, int64_t ldo,
                                const float* bias, const float* ln_sums, int ln_parts, float ln_eps,
-                               const float* col_s, const float* head_gamma, int norm_heads, int dh, int M, int N,
-                               int K, int flags, void* stream);
+                               const float* col_s, const float* head_gamma, int norm_heads, int dh, float head_eps,
+                               int M, int N, int K, int flags, void* stream);
 
 /*
  * The same normalisation on any row-major bf16 buffer: the `nheads` consecutive dh-wide heads that start at column 0
@@ -154,6 +157,9 @@ int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void* W, int64_
  * gamma fp32 [nheads][dh].  ld in elements, multiple of 8; buf 16-byte aligned.
  */
 int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, void* stream);
+/* ... and its LayerNorm (no bias) flavour: (v - mean) * rsqrt(var + eps) * gamma[h, d] over each dh-wide head. */
+int b200vit_layernorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, float eps,
+                            void* stream);
 
 /*
  * NaViT token assembly on the packed [T, D] matrix (na_vit.py:228,350-359): x = LayerNorm(y; gamma, no bias)

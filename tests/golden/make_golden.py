@@ -173,7 +173,43 @@ def make_navit_config5() -> None:
           f"{os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def make_navit_nested() -> None:
+    """Nested-tensor NaViT (reference na_vit_nested_tensor.py): 6 images of 5 resolutions, with and without the q / k
+    LayerNorm.  The reference runs its jagged-batch forward (torch.nested + SDPA) on CPU."""
+    from vit_pytorch.na_vit_nested_tensor import NaViT
+    for name, qk in (("navit_nested_tiny", True), ("navit_nested_noqknorm", False)):
+        kwargs = dict(image_size=64, patch_size=8, num_classes=11, dim=128, depth=2, heads=2, mlp_dim=192, dim_head=64,
+                      qk_rmsnorm=qk)
+        torch.manual_seed(11)
+        model = NaViT(**kwargs).eval()
+        g = torch.Generator().manual_seed(1011)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if p.dim() == 1 and n.endswith("weight"):               # every LayerNorm scale (incl. the per-head ones)
+                    p.add_(0.1 * torch.randn(p.shape, generator=g))
+                elif p.dim() == 1 and n.endswith("bias"):
+                    p.add_(0.05 * torch.randn(p.shape, generator=g))
+                p.copy_(p.bfloat16().float())
+        torch.manual_seed(111)
+        sizes = [(64, 64), (32, 48), (8, 8), (64, 16), (24, 40), (48, 48)]
+        imgs = [torch.randn(3, h, w).bfloat16() for h, w in sizes]
+        with torch.inference_mode():
+            fp32 = model([im.float() for im in imgs])
+            bf16 = model.bfloat16()([im for im in imgs])
+        blob = {"name": name, "kind": "navit_nested", "kwargs": kwargs,
+                "state_dict": {k: v.bfloat16() for k, v in model.state_dict().items()}, "images": imgs,
+                "logits_fp32": fp32.clone(), "logits_ref_bf16": bf16.float().clone(),
+                "versions": {"torch": str(torch.__version__), "reference": "vit-pytorch 1.23.6 @ /root/reference"}}
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(blob, path)
+        print(f"{name}: logits {tuple(fp32.shape)} |max| {fp32.abs().max():.4f}; ref-bf16 max err "
+              f"{(bf16.float() - fp32).abs().max():.5f}; {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "navit_nested":
+        make_navit_nested()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "navit_config5":
         make_navit_config5()
         sys.exit(0)
@@ -185,3 +221,4 @@ if __name__ == "__main__":
         make(n, s)
     make_navit()
     make_navit_config5()
+    make_navit_nested()

@@ -70,3 +70,49 @@ def test_flash_variant_accepts_other_resolutions():
             fused = m(img)
             eager = m.forward_eager(img)
         assert (fused.float() - eager.float()).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("name", ["navit_nested_tiny", "navit_nested_noqknorm"])
+@pytest.mark.parametrize("mode", ["fold", "exact"])
+def test_navit_nested_fused_against_reference_golden(name, mode, monkeypatch):
+    """Nested-tensor NaViT front-end (reference na_vit_nested_tensor.py) on the padding-free fused path: per-head
+    LayerNorm of q / k as the QKV GEMM's epilogue (EPI_HEADLN), varlen attention with scale dim_head ** -0.5."""
+    monkeypatch.setenv("B200VIT_LN_MODE", mode)
+    from vit_pytorch_b200.na_vit_nested_tensor import NaViT
+    g = load_golden(name)
+    m = NaViT(**g["kwargs"]).eval()
+    m.load_state_dict(g["state_dict"])
+    m = m.to(DEV, torch.bfloat16)
+    imgs = [im.to(DEV) for im in g["images"]]
+    _lib.reset_launch_count()
+    with torch.inference_mode():
+        assert m.fused_reason(imgs) is None, m.fused_reason(imgs)
+        out = m(imgs)
+    assert _lib.launch_count() > 0
+    ref = g["logits_fp32"]
+    d = (out.float().cpu() - ref).abs()
+    floor = (g["logits_ref_bf16"] - ref).abs()
+    print(f"{name} [{mode}]: fused max {d.max():.5f} mean {d.mean():.5f}; reference-bf16 max {floor.max():.5f} "
+          f"mean {floor.mean():.5f}")
+    assert out.shape == ref.shape and torch.isfinite(out.float()).all()
+    assert d.mean() <= floor.mean() * 1.05 + 1e-4 and d.max() <= floor.max() * 1.5 + 1e-3
+
+
+@pytest.mark.parametrize("M", [300, 2048])
+def test_gemm_head_layernorm_epilogue(M):
+    """EPI_HEADLN: (v - mean) * rsqrt(var + eps) * gamma per 64-wide head, in the GEMM epilogue (M >= 1024) and in the
+    stand-alone kernel (small M) -- against torch on the bf16-rounded projection."""
+    torch.manual_seed(M)
+    K, H = 128, 3
+    N = 3 * H * 64
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(2 * H * 64, device=DEV)).contiguous()
+    out = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm_headnorm(a, w, out_bf16=out, head_gamma=gamma, norm_heads=2 * H, head_layernorm_eps=1e-5)
+    y = (a.float() @ w.float().t()).bfloat16().float()
+    ref = y.clone()
+    yn = torch.nn.functional.layer_norm(y[:, : 2 * H * 64].reshape(M, 2 * H, 64), (64,), None, None, 1e-5)
+    ref[:, : 2 * H * 64] = (yn * gamma.view(2 * H, 64)).reshape(M, -1)
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2)
+    assert torch.equal(out[:, 2 * H * 64:], y[:, 2 * H * 64:].bfloat16())          # the v third is untouched

@@ -101,3 +101,45 @@ def test_refresh_fused_weights_invalidates_prepared_copies():
     k1 = engine._version_key(ps)
     m.load_state_dict(m.state_dict())
     assert engine._version_key(ps) != k1                            # load_state_dict refreshes on its own
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nested-tensor NaViT front-end (reference na_vit_nested_tensor.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["navit_nested_tiny", "navit_nested_noqknorm"])
+def test_navit_nested_dropin_equals_reference_golden(name):
+    from vit_pytorch_b200.na_vit_nested_tensor import NaViT
+    g = load_golden(name)
+    m = NaViT(**g["kwargs"]).eval()
+    assert list(m.state_dict().keys()) == list(g["state_dict"].keys())
+    m.load_state_dict(g["state_dict"])
+    m = m.float()
+    imgs = [im.float() for im in g["images"]]
+    with torch.inference_mode():
+        out = m(imgs)
+    assert out.shape == g["logits_fp32"].shape
+    assert torch.allclose(out, g["logits_fp32"], rtol=1e-4, atol=2e-5), (out - g["logits_fp32"]).abs().max()
+    assert m.fused_reason(imgs) == "input is not on a CUDA device"
+
+
+def test_navit_nested_same_seed_init_and_signature_equal_the_reference():
+    if not reference_available():
+        pytest.skip("reference checkout not present")
+    import_reference()
+    ref_cls = importlib.import_module("vit_pytorch.na_vit_nested_tensor").NaViT
+    from vit_pytorch_b200.na_vit_nested_tensor import NaViT
+    pr = inspect.signature(ref_cls.__init__).parameters
+    po = inspect.signature(NaViT.__init__).parameters
+    assert list(pr) == list(po)
+    for k in pr:
+        if k != "self":
+            assert pr[k].default == po[k].default, k
+    kw = dict(image_size=32, patch_size=8, num_classes=5, dim=64, depth=1, heads=1, mlp_dim=64)
+    torch.manual_seed(5)
+    a = ref_cls(**kw)
+    torch.manual_seed(5)
+    b = NaViT(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k

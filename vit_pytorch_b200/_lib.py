@@ -21,6 +21,7 @@ EPI_GELU = 2
 EPI_RESIDUAL = 4
 EPI_LNFOLD = 8
 EPI_STATS = 16
+EPI_HEADLN = 64
 
 # every symbol include/b200vit.h declares (tests check that the library exports each of them)
 SYMBOLS = [
@@ -29,7 +30,7 @@ SYMBOLS = [
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
     "b200vit_patchify_varlen_ln", "b200vit_rmsnorm_heads", "b200vit_embed_varlen",
-    "b200vit_gemm_headnorm_bf16",
+    "b200vit_gemm_headnorm_bf16", "b200vit_layernorm_heads",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -61,8 +62,10 @@ def lib() -> C.CDLL:
     L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
                                     vp]
     L.b200vit_gemm_headnorm_bf16.restype = i32
-    L.b200vit_gemm_headnorm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
-                                             i32, i32, vp]
+    L.b200vit_gemm_headnorm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, f32, vp, vp, i32, i32, f32, i32,
+                                             i32, i32, i32, vp]
+    L.b200vit_layernorm_heads.restype = i32
+    L.b200vit_layernorm_heads.argtypes = [vp, i64, vp, i32, i32, i32, f32, vp]
     L.b200vit_stats_parts.restype = i32
     L.b200vit_stats_parts.argtypes = [i32]
     L.b200vit_layernorm.restype = i32
@@ -220,8 +223,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
 def gemm_headnorm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: torch.Tensor, head_gamma: torch.Tensor,
                   norm_heads: int, dh: int = 64, bias: Optional[torch.Tensor] = None,
                   ln_sums: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
-                  col_s: Optional[torch.Tensor] = None) -> None:
-    """out = epilogue(a @ w^T) with the first norm_heads heads of every row RMS-normalised (NaViT q / k norm)."""
+                  col_s: Optional[torch.Tensor] = None, head_layernorm_eps: Optional[float] = None) -> None:
+    """out = epilogue(a @ w^T) with the first norm_heads heads of every row RMS-normalised (NaViT q / k norm), or --
+    head_layernorm_eps given -- LayerNorm-ed without bias (nested-tensor NaViT)."""
     _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w"); _chk(out_bf16, torch.bfloat16, "out_bf16")
     for nm, t in (("bias", bias), ("ln_sums", ln_sums), ("col_s", col_s), ("head_gamma", head_gamma)):
         _chk(t, torch.float32, nm)
@@ -237,10 +241,15 @@ def gemm_headnorm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: torch.Tensor, h
         flags |= EPI_LNFOLD
         assert ln_sums.is_contiguous() and ln_sums.shape[0] == M and ln_sums.shape[-1] == 2
         ln_parts = 1 if ln_sums.dim() == 2 else ln_sums.shape[1]
+    head_eps = 0.0
+    if head_layernorm_eps is not None:
+        flags |= EPI_HEADLN
+        head_eps = float(head_layernorm_eps)
     with _Timed("gemm", M=M, N=N, K=K, flags=flags | 32, flops=2.0 * M * N * K):
         rc = lib().b200vit_gemm_headnorm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16),
                                               out_bf16.stride(0), _ptr(bias), _ptr(ln_sums), ln_parts, float(ln_eps),
-                                              _ptr(col_s), _ptr(head_gamma), norm_heads, dh, M, N, K, flags, _stream())
+                                              _ptr(col_s), _ptr(head_gamma), norm_heads, dh, head_eps, M, N, K, flags,
+                                              _stream())
     _check(rc, "b200vit_gemm_headnorm_bf16")
 
 

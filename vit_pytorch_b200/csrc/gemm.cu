@@ -394,16 +394,20 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 }
 
 extern "C" int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, void* stream);
+extern "C" int b200vit_layernorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, float eps,
+                                       void* stream);
 
 extern "C" int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16,
                                           int64_t ldo, const float* bias, const float* ln_sums, int ln_parts,
                                           float ln_eps, const float* col_s, const float* head_gamma, int norm_heads,
-                                          int dh, int M, int N, int K, int flags, void* stream) {
+                                          int dh, float head_eps, int M, int N, int K, int flags, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(out_bf16 && head_gamma, "gemm_headnorm: null pointer");
   B200_CHECK_ARG(dh == 64, "gemm_headnorm: dim_head=%d not supported by this build (only 64)", dh);
   B200_CHECK_ARG(norm_heads > 0 && norm_heads * 64 <= N, "gemm_headnorm: %d heads do not fit N=%d", norm_heads, N);
-  B200_CHECK_ARG((flags & ~(B200VIT_EPI_BIAS | B200VIT_EPI_LNFOLD)) == 0, "gemm_headnorm: unsupported flags %d", flags);
+  B200_CHECK_ARG((flags & ~(B200VIT_EPI_BIAS | B200VIT_EPI_LNFOLD | B200VIT_EPI_HEADLN)) == 0,
+                 "gemm_headnorm: unsupported flags %d", flags);
+  const bool hln = (flags & B200VIT_EPI_HEADLN) != 0;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(head_gamma) & 15) == 0, "gemm_headnorm: head_gamma must be 16-byte aligned");
   // fused: the CTA-pair kernel's bf16 epilogue, where one warp holds one whole head of its 32 rows
   if (M > 0 && N > 0 && K > 0 && A && W && gemm2_eligible(M, N, K, ldo, flags, out_bf16, nullptr, nullptr) &&
@@ -414,10 +418,11 @@ extern "C" int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void
     B200_CHECK_ARG((lda & 7) == 0 && (ldw & 7) == 0 && lda >= K && ldw >= K && ldo >= N, "gemm_headnorm: bad strides");
     return launch_gemm2(A, lda, W, ldw, out_bf16, nullptr, ldo, bias, nullptr, ln_sums, ln_parts, ln_eps, col_s,
                         nullptr, M, N, K, flags | B200VIT_EPI_HEADNORM, reinterpret_cast<cudaStream_t>(stream),
-                        head_gamma, norm_heads * 64);
+                        head_gamma, norm_heads * 64, head_eps);
   }
   int rc = b200vit_gemm_bf16(A, lda, W, ldw, out_bf16, nullptr, ldo, bias, nullptr, ln_sums, ln_parts, ln_eps, col_s,
-                             nullptr, M, N, K, flags, stream);
+                             nullptr, M, N, K, flags & ~B200VIT_EPI_HEADLN, stream);
   if (rc) return rc;
+  if (hln) return b200vit_layernorm_heads(out_bf16, ldo, head_gamma, M, norm_heads, dh, head_eps, stream);
   return b200vit_rmsnorm_heads(out_bf16, ldo, head_gamma, M, norm_heads, dh, stream);
 }

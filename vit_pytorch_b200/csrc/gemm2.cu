@@ -61,8 +61,9 @@ struct Gemm2Params {
   float ln_inv_dim, ln_eps;
   const float* col_s;
   float* stats_out;  // MODE_DUAL: [M][stats_parts][2] partial (sum, sum of squares) of the bf16-rounded output rows
-  const float* head_gamma;  // EPI_HEADNORM: fp32 [norm_cols] scale of the RMS-normalised leading heads
+  const float* head_gamma;  // EPI_HEADNORM: fp32 [norm_cols] scale of the normalised leading heads
   int norm_cols;            //               columns [0, norm_cols) are normalised per 64-wide head
+  float head_eps;           // EPI_HEADLN:   epsilon of the per-head LayerNorm (instead of the RMS norm)
 };
 
 // LN-fold, bias and GELU on W consecutive accumulator columns starting at col0 (W = 16 or 32), on fp32 PAIRS (FFMA2):
@@ -368,6 +369,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
 
         float ss = 0.f;  // EPI_HEADNORM: sum of squares of this row's 64 (bf16-rounded) values = one head
+        float hs = 0.f;  // EPI_HEADLN: their sum
         auto emit16 = [&](const uint32_t (&r)[16], int cidx) {
           float v[16];
 #pragma unroll
@@ -384,6 +386,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 4; ++i) {
                 const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xFFFF0000u);
                 ss = fmaf(lo, lo, fmaf(hi, hi, ss));
+                if (flags & B200VIT_EPI_HEADLN) hs += lo + hi;
               }
             }
           }
@@ -402,7 +405,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         emit16(rb, 3);
         if ((flags & B200VIT_EPI_HEADNORM) && col_base < p.norm_cols) {
           // this warp's 64 columns are exactly one head: every thread rescales its own row inside the staging box
-          const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);  // sqrt(dh) / max(||v||, eps)
+          // RMS norm: v * sqrt(dh) / max(||v||, eps) * gamma;  LayerNorm (no bias): (v - mean) * rsqrt(var + eps) * gamma
+          const bool hln = (flags & B200VIT_EPI_HEADLN) != 0;
+          const float mean = hln ? hs * (1.0f / 64.0f) : 0.f;
+          const float inv = hln ? rsqrtf(fmaxf(ss * (1.0f / 64.0f) - mean * mean, 0.f) + p.head_eps)
+                                : 8.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t sp = my_row0_s + ((static_cast<uint32_t>(q) ^ sw) << 4);
@@ -416,7 +423,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
-              o[i] = pack_bf16x2(lo * inv * gg[2 * i], hi * inv * gg[2 * i + 1]);
+              o[i] = pack_bf16x2((lo - mean) * inv * gg[2 * i], (hi - mean) * inv * gg[2 * i + 1]);
             }
             sts_v4(sp, o[0], o[1], o[2], o[3]);
           }
@@ -591,7 +598,7 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
                  const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
                  const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream,
-                 const float* head_gamma, int norm_cols) {
+                 const float* head_gamma, int norm_cols, float head_eps) {
   using namespace g2;
   const bool dual = out_bf16 && out_f32;
   Gemm2Params p{};
@@ -610,6 +617,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.col_s = col_s;
   p.head_gamma = head_gamma;
   p.norm_cols = norm_cols;
+  p.head_eps = head_eps;
 
   CUtensorMap tmA, tmB, tmOut, tmResid, tmOutB;
   {
@@ -659,7 +667,8 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   const int ew_force = g_gemm_ew.load();
   const bool ew4 = ew_force == 4 || (ew_force == 0 && K >= 2048);
   constexpr int F_BIAS = B200VIT_EPI_BIAS, F_GELU = B200VIT_EPI_GELU, F_RES = B200VIT_EPI_RESIDUAL,
-                F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS, F_HN = B200VIT_EPI_HEADNORM;
+                F_FOLD = B200VIT_EPI_LNFOLD, F_STATS = B200VIT_EPI_STATS, F_HN = B200VIT_EPI_HEADNORM,
+                F_HLN = B200VIT_EPI_HEADLN;
   // the flag combinations of a transformer block get their own instantiation, anything else the generic kernel
   if (dual) {
     if (flags == (F_BIAS | F_RES | F_STATS))
@@ -672,6 +681,7 @@ int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   if (out_f32) return ew4 ? B200_G2_LAUNCH_EW(MODE_F32, -1, 4) : B200_G2_LAUNCH(MODE_F32, -1);
   if (flags & F_HN) {  // (only reached through b200vit_gemm_headnorm_bf16)
     if (flags == (F_HN | F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_HN | F_FOLD | F_BIAS);
+    if (flags == (F_HN | F_HLN | F_FOLD | F_BIAS)) return B200_G2_LAUNCH(MODE_BF16, F_HN | F_HLN | F_FOLD | F_BIAS);
     if (flags == F_HN) return B200_G2_LAUNCH(MODE_BF16, F_HN);
     return B200_G2_LAUNCH(MODE_BF16, -1);
   }

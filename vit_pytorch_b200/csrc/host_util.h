@@ -48,7 +48,7 @@ int gemm2_eligible(int M, int N, int K, int64_t ldo, int flags, const void* out_
 int launch_gemm2(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32, int64_t ldo,
                  const float* bias, const float* resid, const float* ln_sums, int ln_parts, float ln_eps,
                  const float* col_s, float* stats_out, int M, int N, int K, int flags, cudaStream_t stream,
-                 const float* head_gamma = nullptr, int norm_cols = 0);
+                 const float* head_gamma = nullptr, int norm_cols = 0, float head_eps = 0.f);
 void gemm_force_version(int v);
 void gemm2_force_epilogue_warps(int v);
 void attention_varlen_set_mode(int v);

@@ -523,10 +523,12 @@ namespace b200 {
 // One warp per token; 8 lanes per head (8 bf16 = 16 B each), so four heads are normalised per step with a 3-step
 // butterfly inside each 8-lane group; the loads of U steps are issued before the first reduction (a serial
 // load -> shuffle -> store chain per step left the kernel latency bound at a quarter of the HBM rate).
-template <int U>
+// LN = true: LayerNorm over the head's 64 values without bias, (v - mean) * rsqrt(var + eps) * gamma -- the q / k norm
+// of the nested-tensor NaViT (na_vit_nested_tensor.py:61-62,101-102) -- instead of the RMS norm.
+template <int U, bool LN>
 __global__ void __launch_bounds__(256)
 rmsnorm_heads_kernel(__nv_bfloat16* __restrict__ buf, long long ld, const float* __restrict__ gamma, int T,
-                     int nheads) {
+                     int nheads, float eps) {
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
@@ -544,16 +546,29 @@ rmsnorm_heads_kernel(__nv_bfloat16* __restrict__ buf, long long ld, const float*
       const int hh = base + 4 * u + grp;
       __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw[u]);
       float2 f[4];
-      float ss = 0.f;
+      float ss = 0.f, s1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         f[i] = __bfloat1622float2(h2[i]);
         ss = fmaf(f[i].x, f[i].x, fmaf(f[i].y, f[i].y, ss));
+        s1 += f[i].x + f[i].y;
       }
       ss += __shfl_xor_sync(0xffffffffu, ss, 4);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
+      float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
+      if (LN) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        const float mean = s1 * (1.0f / 64.0f);
+        inv = rsqrtf(fmaxf(ss * (1.0f / 64.0f) - mean * mean, 0.f) + eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[i].x -= mean;
+          f[i].y -= mean;
+        }
+      }
       if (hh < nheads) {
         const float4 g0 = *reinterpret_cast<const float4*>(gamma + hh * 64 + 8 * sub);
         const float4 g1 = *reinterpret_cast<const float4*>(gamma + hh * 64 + 8 * sub + 4);
@@ -688,6 +703,21 @@ embed_varlen_kernel(const float* __restrict__ y, const float* __restrict__ gamma
 
 }  // namespace b200
 
+extern "C" int b200vit_layernorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh, float eps,
+                                       void* stream) {
+  B200_CHECK_ARG(buf && gamma && T > 0 && nheads > 0, "layernorm_heads: bad argument");
+  B200_CHECK_ARG(dh == 64, "layernorm_heads: dim_head=%d not supported by this build (only 64)", dh);
+  B200_CHECK_ARG(ld >= (int64_t)nheads * 64 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
+                 "layernorm_heads: rows must be 16-byte aligned and hold nheads*64 columns (ld=%lld)", (long long)ld);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto b = reinterpret_cast<__nv_bfloat16*>(buf);
+  if (nheads > 8) b200::rmsnorm_heads_kernel<4, true><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads, eps);
+  else b200::rmsnorm_heads_kernel<2, true><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}
+
 extern "C" int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, int T, int nheads, int dh,
                                      void* stream) {
   B200_CHECK_ARG(buf && gamma && T > 0 && nheads > 0, "rmsnorm_heads: bad argument");
@@ -696,8 +726,8 @@ extern "C" int b200vit_rmsnorm_heads(void* buf, int64_t ld, const float* gamma, 
                  "rmsnorm_heads: rows must be 16-byte aligned and hold nheads*64 columns (ld=%lld)", (long long)ld);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto b = reinterpret_cast<__nv_bfloat16*>(buf);
-  if (nheads > 8) b200::rmsnorm_heads_kernel<4><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads);
-  else b200::rmsnorm_heads_kernel<2><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads);
+  if (nheads > 8) b200::rmsnorm_heads_kernel<4, false><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads, 0.f);
+  else b200::rmsnorm_heads_kernel<2, false><<<(T + 7) / 8, 256, 0, st>>>(b, ld, gamma, T, nheads, 0.f);
   B200_CHECK_CUDA(cudaGetLastError());
   b200::count_launch();
   return 0;
