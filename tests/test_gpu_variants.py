@@ -115,4 +115,5 @@ def test_gemm_head_layernorm_epilogue(M):
     yn = torch.nn.functional.layer_norm(y[:, : 2 * H * 64].reshape(M, 2 * H, 64), (64,), None, None, 1e-5)
     ref[:, : 2 * H * 64] = (yn * gamma.view(2 * H, 64)).reshape(M, -1)
     assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2)
-    assert torch.equal(out[:, 2 * H * 64:], y[:, 2 * H * 64:].bfloat16())          # the v third is untouched
+    # the v third is the plain projection (accumulation order differs from torch's: compare within a bf16 ulp)
+    assert torch.allclose(out[:, 2 * H * 64:].float(), y[:, 2 * H * 64:], rtol=1e-2, atol=1e-2)
