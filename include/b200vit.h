@@ -105,6 +105,7 @@ int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, in
  *   qkv[B*N, 3*H*dh] bf16 (columns: [q | k | v], each head-major h*dh + d; vit.py:54-55)
  *   out[B*N, H*dh]   bf16 (merged heads, vit.py:63) = softmax(q k^T * scale) v          (vit.py:57-62)
  * One pass over the keys (N <= 512): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ * dh = 64, or 80 (canonical ViT-H/14): an 80-wide head is staged as a 64-wide + a 16-wide shared-memory slab.
  * N <= 224: software-pipelined kernel (attention_pipe.cu: two score regions + one O slot per SM, K/V once per head).
  */
 int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
@@ -195,6 +196,7 @@ int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* strea
  *   key 4: GEMM kernel choice: 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies
  *   key 11: varlen attention kernel: 0 = pipelined 64-key blocks (default), 1 = serial 128-key blocks
  *   key 12: fp32-epilogue warps of the CTA-pair GEMM: 0 = auto (4 when K >= 2048, else 8), 4 / 8 = forced
+ *   key 14 / 15: dim_head 80: LBO / SBO bytes of the 16-wide V slab descriptor (bring-up probe)
  *   key 13: pipelined attention: 0 = all softmax exponentials on MUFU (default), 1 = half of them on the FMA pipe
  */
 int b200vit_debug_set(int key, int value);

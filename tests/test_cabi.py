@@ -41,8 +41,8 @@ def test_version_and_launch_counter(lib):
 def test_bad_arguments_return_error_codes(lib):
     rc = lib.b200vit_gemm_bf16(None, 8, None, 8, None, None, 8, None, None, None, 0, 1e-5, None, None, 1, 1, 8, 0, None)
     assert rc == -1 and b"null" in lib.b200vit_last_error()
-    rc = lib.b200vit_attention(ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 16, 1, 80, 0.1, None)
-    assert rc == -1 and b"dim_head=80" in lib.b200vit_last_error()
+    rc = lib.b200vit_attention(ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 16, 1, 96, 0.1, None)
+    assert rc == -1 and b"dim_head=96" in lib.b200vit_last_error()
     rc = lib.b200vit_attention(ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 4096, 1, 64, 0.1, None)
     assert rc == -1 and b"512" in lib.b200vit_last_error()     # single-pass kernel; longer: b200vit_attention_varlen
     rc = lib.b200vit_patchify_ln(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256),

@@ -262,6 +262,23 @@ def test_attention_kernel_variants_agree(knob, value, B, N):
     assert within(out, ref_out.float().cpu(), rtol=2e-2, atol=2e-3) > 0.999
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 257, 16), (3, 197, 4), (5, 64, 2), (2, 400, 3), (1, 512, 2), (40, 129, 5)])
+def test_attention_dim_head_80(B, N, H):
+    """Canonical ViT-H/14 head width (reference vit.py:86 `dim_head`): 64-wide + 16-wide shared-memory slabs."""
+    torch.manual_seed(N)
+    dh = 80
+    I = H * dh
+    qkv = torch.randn(B * N, 3 * I, device=DEV).bfloat16()
+    out = torch.zeros(B * N, I, device=DEV, dtype=torch.bfloat16)
+    _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
+    q, k, v = qkv.float().cpu().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = (O.softmax_last((q @ k.transpose(-1, -2)) * dh ** -0.5) @ v).permute(0, 2, 1, 3).reshape(B * N, I)
+    d = (out.float().cpu() - ref).abs().view(B * N, H, dh)
+    print(f"dh80 B{B} N{N}: max err dims 0..63 {d[..., :64].max():.4f}, dims 64..79 {d[..., 64:].max():.4f}")
+    assert within(out, ref) > 0.995
+    assert (out.float().cpu() - ref).abs().max() < 2e-2
+
+
 def test_attention_is_deterministic_and_batch_invariant():
     """The persistent kernel strides units over CTAs: the same (image, head) must give the same bits wherever it
     lands in the batch and on repeated launches."""

@@ -133,6 +133,9 @@ def test_vit_b16_against_oracle(kind):
      0.0249, 0.525),
     ("ViT-H/14", dict(image_size=224, patch_size=14, num_classes=1000, dim=1280, depth=32, heads=16, mlp_dim=5120),
      0.0257, 0.478),
+    # the canonical ViT-H/14 head width: dim_head = 80 (SURVEY.md 8d config 4 "run with dim_head=64 and 80")
+    ("ViT-H/14 dim_head 80", dict(image_size=224, patch_size=14, num_classes=1000, dim=1280, depth=32, heads=16,
+                                  mlp_dim=5120, dim_head=80), 0.0298, 0.478),
 ])
 def test_large_configs_against_oracle(name, kwargs, floor_max, floor_frac):
     torch.manual_seed(0)

@@ -30,6 +30,7 @@ struct AttnParams {
   float scale_log2e;
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
+  unsigned v16_lbo, v16_sbo;  // dim_head 80: descriptor strides of the 16-wide V slab (32-byte swizzle)
 };
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
@@ -39,18 +40,27 @@ __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { ret
 // other one's softmax keeps the MUFU / issue slots busy.
 // (The round-1 experiments -- FMA-pipe exp2, split PV accumulation, skipped row max, 8 warps per tile, globaltimer
 // traces -- are recorded in profiles/r01*; their code is gone.  Shapes with N <= 224 run attention_pipe.cu instead.)
-template <int NWG, int STAGES, int TMEM_COLS>
+//
+// DH = 64 or 80 (canonical ViT-H/14, reference vit.py:86 `dim_head`).  128-byte swizzled TMA boxes are 64 bf16 wide, so
+// an 80-wide head is staged as a 64-wide slab plus a 16-wide slab (32-byte rows, 32-byte swizzle): Q K^T gets a
+// fifth k-step from the 16-wide slabs, P V a second MMA per key step with N = 16 into O columns [64, 80).
+template <int NWG, int STAGES, int TMEM_COLS, int DH>
 __global__ void __launch_bounds__((4 * NWG + 2) * 32, TMEM_COLS == 256 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmQ16, const __grid_constant__ CUtensorMap tmKV16,
                  const AttnParams p) {
+  static_assert(DH == 64 || DH == 80, "dim_head 64 or 80");
+  constexpr bool X16 = DH == 80;  // the extra 16-wide slabs exist
   constexpr int REGION = TMEM_COLS / NWG;
-  constexpr int O_COL = REGION - ATT_DH;
+  constexpr int O_COL = REGION - DH;
   constexpr int NUM_SOFTMAX_WARPS = 4 * NWG;
-  constexpr int Q_TILE_BYTES = 128 * 128;
+  constexpr int Q_TILE_BYTES = 128 * 128 + (X16 ? 128 * 32 : 0);  // [128 x 64] slab, then [128 x 16] slab
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int kv_bytes = att_kv_bytes(p.kv_boxes, p.kv_box_rows);  // multiple of 1024
+  const int kv64_bytes = att_kv_bytes(p.kv_boxes, p.kv_box_rows);  // multiple of 1024
+  const int kv16_bytes = X16 ? p.kv_boxes * p.kv_box_rows * 32 : 0;   // multiple of 256 (8-row atoms of 32 bytes)
+  const int kv_bytes = kv64_bytes + (X16 ? (kv16_bytes + 1023) / 1024 * 1024 : 0);  // K (or V): 64-slab, 16-slab
   const int stage_bytes = 2 * kv_bytes + NWG * Q_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* full_bar = bars;
@@ -69,6 +79,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    if (X16) {
+      tma_prefetch_desc(&tmQ16);
+      tma_prefetch_desc(&tmKV16);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -104,21 +118,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint8_t* sk = smem + s * stage_bytes;
         uint8_t* sv = sk + kv_bytes;
         uint8_t* sq = sv + kv_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        // bytes that will land: the TMA boxes, not the (1024-aligned) slab sizes
+        mbar_arrive_expect_tx(&full_bar[s], 2 * (kv64_bytes + kv16_bytes) + NWG * Q_TILE_BYTES);
         for (int i = 0; i < p.kv_boxes; ++i) {
-          tma_load_3d(sk + i * p.kv_box_rows * 128, &tmKV, &full_bar[s], p.I + h * ATT_DH, i * p.kv_box_rows, b);
-          tma_load_3d(sv + i * p.kv_box_rows * 128, &tmKV, &full_bar[s], 2 * p.I + h * ATT_DH, i * p.kv_box_rows, b);
+          tma_load_3d(sk + i * p.kv_box_rows * 128, &tmKV, &full_bar[s], p.I + h * DH, i * p.kv_box_rows, b);
+          tma_load_3d(sv + i * p.kv_box_rows * 128, &tmKV, &full_bar[s], 2 * p.I + h * DH, i * p.kv_box_rows, b);
+          if (X16) {
+            tma_load_3d(sk + kv64_bytes + i * p.kv_box_rows * 32, &tmKV16, &full_bar[s], p.I + h * DH + 64,
+                        i * p.kv_box_rows, b);
+            tma_load_3d(sv + kv64_bytes + i * p.kv_box_rows * 32, &tmKV16, &full_bar[s], 2 * p.I + h * DH + 64,
+                        i * p.kv_box_rows, b);
+          }
         }
         for (int t = 0; t < NWG; ++t) {
           const int qt = round * NWG + t;  // may be >= q_tiles: box fully out of bounds -> zeros
-          tma_load_3d(sq + t * Q_TILE_BYTES, &tmQ, &full_bar[s], h * ATT_DH, qt * 128, b);
+          tma_load_3d(sq + t * Q_TILE_BYTES, &tmQ, &full_bar[s], h * DH, qt * 128, b);
+          if (X16) tma_load_3d(sq + t * Q_TILE_BYTES + 128 * 128, &tmQ16, &full_bar[s], h * DH + 64, qt * 128, b);
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);  // B = V is MN-major
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);    // B = V is MN-major
+      const uint32_t idesc_pv16 = make_idesc_bf16(128, 16, 0, 1);  // dim_head 80: the 16-wide V slab
       // S_t(it) = Q_t K^T into region t  (waits until the epilogue of unit it-1 has drained the region)
       auto issue_s = [&](int it, int t) {
         const int s = it % STAGES;
@@ -133,7 +156,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint64_t adesc = make_smem_desc_sw128(sq + t * Q_TILE_BYTES, 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(sk + n0 * 128, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_ss(d_s + n0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          if (X16) {
+            // fifth k-step (dims 64..79): K-major slabs with 32-byte rows, 32-byte swizzle, 8-row atoms of 256 bytes
+            const uint64_t a16 = make_smem_desc(sq + t * Q_TILE_BYTES + 128 * 128, 16, 256, 6);
+            const uint64_t b16 = make_smem_desc(sk + kv64_bytes + n0 * 32, 16, 256, 6);
+            umma_ss(d_s + n0, a16, b16, idesc_s, 1);
+          }
         }
         umma_commit(&s_full[t]);
       };
@@ -148,6 +177,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, p.v_lbo, p.v_sbo);
           umma_ts(d_o, tmem_base + t * REGION + k * 8, vdesc, idesc_pv, k != 0);
+          if (X16) {  // O[:, 64:80] += P_k V_k[:, 64:80]: 16 keys = two 8-row atoms of 256 bytes
+            const uint64_t v16 = make_smem_desc(sv + kv64_bytes + k * 512, p.v16_lbo, p.v16_sbo, 6);
+            umma_ts(d_o + 64, tmem_base + t * REGION + k * 8, v16, idesc_pv16, k != 0);
+          }
         }
         umma_commit(&o_full[t]);
       };
@@ -300,25 +333,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float inv = 1.0f / sum;
       mbar_wait(&o_full[t], up);
       tc_fence_after();
-      uint32_t ob[32];  // 64 output columns as packed bf16 pairs
+      uint32_t ob[DH / 2];  // DH output columns as packed bf16 pairs
       if (warp_active) {
-        uint32_t r0[32];
+        if constexpr (!X16) {
+          uint32_t r0[32];
 #pragma unroll
-        for (int hcol = 0; hcol < 2; ++hcol) {
-          tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
-          tmem_ld_wait();
+          for (int hcol = 0; hcol < 2; ++hcol) {
+            tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+            for (int j = 0; j < 16; ++j)
+              ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+          }
+        } else {  // 80 columns: five 16-column groups (O_COL is a multiple of 16, not of 32)
+          uint32_t r0[16];
+#pragma unroll
+          for (int g = 0; g < DH / 16; ++g) {
+            tmem_ld_32x32b_x16(t_lane + O_COL + 16 * g, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ob[8 * g + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
       if (warp_active && qrow < p.N) {
-        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * ATT_DH);
+        uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.N + qrow) * p.I + h * DH);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
+        for (int j = 0; j < DH / 8; ++j) op[j] = make_uint4(ob[4 * j], ob[4 * j + 1], ob[4 * j + 2], ob[4 * j + 3]);
       }
     }
   }
@@ -338,22 +383,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 static std::atomic<int> g_attn_mode{0};
 static std::atomic<int> g_attn_v_lbo{1024};  // V descriptor leading-dim byte offset (bring-up probe)
 static std::atomic<int> g_attn_v_sbo{1024};  // V descriptor stride-dim byte offset
+static std::atomic<int> g_attn_v16_lbo{256};  // dim_head 80: the same two for the 16-wide V slab (bring-up probe)
+static std::atomic<int> g_attn_v16_sbo{256};
 
 bool attention_pipe_eligible(int N, int dh);
 int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
                           cudaStream_t stream);
 
-template <int NWG, int STAGES, int TMEM_COLS = 512>
-static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, size_t smem_bytes,
-                            cudaStream_t stream) {
-  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS>;
+template <int NWG, int STAGES, int TMEM_COLS, int DH>
+static int launch_attention_t(const CUtensorMap* tm, const AttnParams& p, size_t smem_bytes, cudaStream_t stream) {
+  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS, DH>;
   B200_ENSURE_SMEM(kern, smem_bytes);
   const int slots = num_sms() * (TMEM_COLS == 256 ? 2 : 1);
   const int grid = p.units < slots ? p.units : slots;
-  kern<<<grid, (4 * NWG + 2) * 32, smem_bytes, stream>>>(tmQ, tmKV, p);
+  kern<<<grid, (4 * NWG + 2) * 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+template <int NWG, int STAGES, int TMEM_COLS = 512>
+static int launch_attention(const CUtensorMap* tm, int dh, const AttnParams& p, size_t smem_bytes,
+                            cudaStream_t stream) {
+  if (dh == 80) return launch_attention_t<NWG, STAGES, TMEM_COLS, 80>(tm, p, smem_bytes, stream);
+  return launch_attention_t<NWG, STAGES, TMEM_COLS, 64>(tm, p, smem_bytes, stream);
 }
 
 }  // namespace b200
@@ -377,6 +429,8 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 4: gemm_force_version(value); return 0;
     case 12: gemm2_force_epilogue_warps(value); return 0;
     case 13: attention_pipe_set_emul(value); return 0;
+    case 14: g_attn_v16_lbo = value; return 0;
+    case 15: g_attn_v16_sbo = value; return 0;
     case 11: attention_varlen_set_mode(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
@@ -385,7 +439,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
 extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream) {
   B200_CHECK_ARG(qkv && out, "attention: null pointer");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
-  B200_CHECK_ARG(dh == ATT_DH, "attention: dim_head=%d not supported by this build (only 64)", dh);
+  B200_CHECK_ARG(dh == 64 || dh == 80, "attention: dim_head=%d not supported by this build (64 or 80)", dh);
   B200_CHECK_ARG(N <= 512, "attention: N=%d > 512 needs the (unbuilt) online-softmax path", N);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "attention: pointers must be 16-byte aligned");
@@ -409,8 +463,11 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.v_lbo = (unsigned)g_attn_v_lbo.load();
   p.v_sbo = (unsigned)g_attn_v_sbo.load();
+  p.v16_lbo = (unsigned)g_attn_v16_lbo.load();
+  p.v16_sbo = (unsigned)g_attn_v16_sbo.load();
 
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tm[4];  // Q and K/V boxes of 64 columns (128-byte swizzle), and -- dim_head 80 -- of 16 columns (32-byte)
+  CUtensorMap &tmQ = tm[0], &tmKV = tm[1];
   const uint64_t dims[3] = {(uint64_t)3 * p.I, (uint64_t)N, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)3 * p.I * 2, (uint64_t)N * 3 * p.I * 2};
   {
@@ -423,19 +480,31 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
     int rc = encode_tmap_bf16(&tmKV, qkv, 3, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t kv_bytes = (size_t)att_kv_bytes(p.kv_boxes, p.kv_box_rows);
-  const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * 128 * 128;
+  tm[2] = tm[0];
+  tm[3] = tm[1];
+  if (dh == 80) {  // the 16-wide slabs: 32-byte rows, 32-byte swizzle
+    const uint32_t qbox[3] = {16, 128, 1};
+    int rc = encode_tmap_bf16_sw(&tm[2], qkv, 3, dims, strides, qbox, 32);
+    if (rc) return rc;
+    const uint32_t kvbox[3] = {16, (uint32_t)p.kv_box_rows, 1};
+    rc = encode_tmap_bf16_sw(&tm[3], qkv, 3, dims, strides, kvbox, 32);
+    if (rc) return rc;
+  }
+  const size_t kv64 = (size_t)att_kv_bytes(p.kv_boxes, p.kv_box_rows);
+  const size_t kv16 = dh == 80 ? ((size_t)p.kv_boxes * p.kv_box_rows * 32 + 1023) / 1024 * 1024 : 0;
+  const size_t kv_bytes = kv64 + kv16;
+  const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * (128 * 128 + (dh == 80 ? 128 * 32 : 0));
   auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
   // two K/V/Q stages when they fit (prefetch of the next unit), else one; the occupancy-2 variant uses one
   const int stages = (!occ2 && smem_for(2) <= 227 * 1024) ? 2 : 1;
   const size_t smem_bytes = smem_for(stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (occ2 && smem_bytes <= 113 * 1024) return launch_attention<1, 1, 256>(tmQ, tmKV, p, smem_bytes, st);
+  if (occ2 && smem_bytes <= 113 * 1024) return launch_attention<1, 1, 256>(tm, dh, p, smem_bytes, st);
   if (nwg == 2) {
-    if (stages == 1) return launch_attention<2, 1>(tmQ, tmKV, p, smem_bytes, st);
-    return launch_attention<2, 2>(tmQ, tmKV, p, smem_bytes, st);
+    if (stages == 1) return launch_attention<2, 1>(tm, dh, p, smem_bytes, st);
+    return launch_attention<2, 2>(tm, dh, p, smem_bytes, st);
   }
-  if (stages == 1) return launch_attention<1, 1>(tmQ, tmKV, p, smem_bytes, st);
-  return launch_attention<1, 2>(tmQ, tmKV, p, smem_bytes, st);
+  if (stages == 1) return launch_attention<1, 1>(tm, dh, p, smem_bytes, st);
+  return launch_attention<1, 2>(tm, dh, p, smem_bytes, st);
 }

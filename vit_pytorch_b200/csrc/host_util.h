@@ -37,6 +37,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // Encodes a rank-`rank` bf16 tensor map with 128B swizzle.  dims/box innermost first; strides in BYTES for dims 1..
 int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, bool swizzle128 = true);
+// same, with the swizzle width in bytes (0 = none, 32, 64, 128)
+int encode_tmap_bf16_sw(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 int encode_tmap_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, bool swizzle128 = false);
 

@@ -177,8 +177,10 @@ class TransformerEngine:
 
     def unsupported_reason(self, N: int) -> Optional[str]:
         for attn, ff in self._layers():
-            if attn.dim_head != 64:
-                return f"dim_head={attn.dim_head} (the attention kernel is built for 64)"
+            if attn.dim_head not in (64, 80):
+                return f"dim_head={attn.dim_head} (the attention kernels are built for 64 and 80)"
+            if attn.dim_head == 80 and (N > 512 or getattr(attn, "q_norm", None) is not None):
+                return "dim_head=80 is built for the single-pass attention kernel (N <= 512, no q/k norm) only"
             if attn.dim % 8 or ff.hidden_dim % 8:
                 return "dim / mlp_dim not multiples of 8"
         if N > 16384:
