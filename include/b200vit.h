@@ -96,6 +96,21 @@ int b200vit_embed_tokens(const float* y, const float* gamma, const float* beta, 
                          const float* tail, float* x, void* xb_bf16, float* stats, int B, int n, int ncls, int ntail,
                          int D, float eps, void* stream);
 
+/*
+ * im2col-free patch embedding for 16 x 16 patches (vit.py:100-102 without materialising the Rearrange or the
+ * LayerNorm): y[B*n, D] fp32 = LN(patch pixels; gamma, beta) W^T + b, with the A operand of the tcgen05 GEMM loaded
+ * straight out of the NCHW bf16 image by a 5-D TMA tensor map (pixel | pixel row | patch column | patch row |
+ * image x channel), the LayerNorm folded into the epilogue.
+ *   b200vit_patch_stats: stats[B*n][2] = (sum, sum of squares) of each patch's C*256 pixels.
+ *   b200vit_patch_embed_tma: w_perm[D][C*256] bf16 = gamma (.) W with its columns permuted from the reference's
+ *     (p1 p2 c) order to (c p1 p2); bias[D] = W beta + b; col_s[D] = row sums of w_perm; ldo = row stride of out_f32.
+ * H, W multiples of 16 (other patch sizes: b200vit_patchify_ln + b200vit_gemm_bf16).
+ */
+int b200vit_patch_stats(const void* img, float* stats, int B, int C, int H, int W, void* stream);
+int b200vit_patch_embed_tma(const void* img, const void* w_perm, const float* bias, const float* col_s,
+                            const float* patch_stats, float ln_eps, float* out_f32, int64_t ldo, int B, int C, int H,
+                            int W, int D, void* stream);
+
 /* x[M, D] fp32 -> xb bf16 copy + stats[M][2] = (sum, sum of squares) of the bf16-rounded rows: entry into the
  * LN-folded layer chain for token matrices handed to Transformer.forward directly (reference mae.py:74). */
 int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, int D, void* stream);

@@ -136,6 +136,33 @@ def test_patchify_ln(C, H, W, p):
     assert (out[:, pd:] == 0).all()
 
 
+@pytest.mark.parametrize("B,C,H,W,D", [(3, 3, 224, 224, 256), (2, 3, 32, 48, 64), (2, 1, 64, 64, 128), (5, 3, 16, 16, 64),
+                                        (2, 3, 16, 512, 72), (1, 4, 48, 16, 64)])
+def test_patch_embed_tma_matches_patchify_layernorm_linear(B, C, H, W, D):
+    """im2col-free patch embedding: the tcgen05 GEMM reads the NCHW image through a 5-D TMA map, LayerNorm(patch) is
+    folded into its epilogue -- against Rearrange -> LayerNorm -> Linear (vit.py:100-102) in fp32 on the CPU."""
+    torch.manual_seed(H * W + C)
+    pd = C * 256
+    img = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    g, be = 1 + 0.2 * torch.randn(pd), 0.1 * torch.randn(pd)
+    w = (torch.randn(D, pd) / pd ** 0.5).bfloat16().float()
+    b = 0.1 * torch.randn(D)
+    wg = w * g[None, :]
+    w_perm = wg.view(D, 256, C).permute(0, 2, 1).reshape(D, pd).bfloat16().contiguous().to(DEV)
+    col_s = w_perm.float().sum(1).contiguous()
+    bias = (w @ be + b).to(DEV).contiguous()
+    n = (H // 16) * (W // 16)
+    y = torch.full((B * n, D), float("nan"), device=DEV)
+    stats = torch.zeros(B * n, 2, device=DEV)
+    _lib.patch_embed_tma(img, w_perm, bias, col_s, stats, y)
+    patches = O.patchify(img.float().cpu(), 16, 16)                                 # [B, n, (p1 p2 c)]
+    ref = O.linear(O.layer_norm(patches, g, be), w, b).reshape(B * n, D)
+    assert torch.allclose(stats[:, 0].cpu(), patches.reshape(B * n, -1).sum(1), rtol=1e-4, atol=1e-2)
+    d = (y.cpu() - ref).abs()
+    print(f"patch_embed_tma {B}x{C}x{H}x{W} -> {D}: max {d.max():.4f} mean {d.mean():.5f}")
+    assert torch.isfinite(y).all() and d.max() < 3e-2 and d.mean() < 4e-3     # gamma (.) W is rounded to bf16
+
+
 @pytest.mark.parametrize("ncls", [0, 1])
 def test_embed_tokens(ncls):
     torch.manual_seed(6)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "b200vit_attention", "b200vit_mean_pool", "b200vit_cast_f32_bf16", "b200vit_rowstats_cast", "b200vit_debug_set",
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
     "b200vit_patchify_varlen_ln", "b200vit_rmsnorm_heads", "b200vit_embed_varlen",
-    "b200vit_gemm_headnorm_bf16", "b200vit_layernorm_heads",
+    "b200vit_gemm_headnorm_bf16", "b200vit_layernorm_heads", "b200vit_patch_stats", "b200vit_patch_embed_tma",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
     L.b200vit_layernorm.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, f32, vp]
     L.b200vit_patchify_ln.restype = i32
     L.b200vit_patchify_ln.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, vp]
+    L.b200vit_patch_stats.restype = i32
+    L.b200vit_patch_stats.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.b200vit_patch_embed_tma.restype = i32
+    L.b200vit_patch_embed_tma.argtypes = [vp, vp, vp, vp, vp, f32, vp, i64, i32, i32, i32, i32, i32, vp]
     L.b200vit_embed_tokens.restype = i32
     L.b200vit_embed_tokens.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
     L.b200vit_rowstats_cast.restype = i32
@@ -288,6 +292,27 @@ def patchify_ln(img: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_
         rc = lib().b200vit_patchify_ln(_ptr(img), _ptr(gamma), _ptr(beta), _ptr(out_bf16), out_bf16.stride(0), B, Cc,
                                        H, W, ph, pw, float(eps), _stream())
     _check(rc, "b200vit_patchify_ln")
+
+
+def patch_embed_tma(img: torch.Tensor, w_perm: torch.Tensor, bias: torch.Tensor, col_s: torch.Tensor,
+                    stats: torch.Tensor, out_f32: torch.Tensor, eps: float = 1e-5) -> None:
+    """out_f32[B*n, D] = LayerNorm(16x16 patches of img) @ W^T + b, the image read through a 5-D TMA map (no patch
+    matrix in memory).  w_perm / bias / col_s: see include/b200vit.h; stats [B*n, 2] is scratch (fully overwritten)."""
+    _chk(img, torch.bfloat16, "img"); _chk(w_perm, torch.bfloat16, "w_perm"); _chk(out_f32, torch.float32, "out")
+    for nm, t in (("bias", bias), ("col_s", col_s), ("stats", stats)):
+        _chk(t, torch.float32, nm)
+    assert img.is_contiguous() and img.dim() == 4 and w_perm.is_contiguous() and out_f32.stride(1) == 1
+    B, Cc, H, W = img.shape
+    D = w_perm.shape[0]
+    n = (H // 16) * (W // 16)
+    assert w_perm.shape[1] == Cc * 256 and out_f32.shape == (B * n, D) and stats.is_contiguous() and stats.numel() == 2 * B * n
+    with _Timed("patch_stats", bytes=img.numel() * 2):
+        rc = lib().b200vit_patch_stats(_ptr(img), _ptr(stats), B, Cc, H, W, _stream())
+    _check(rc, "b200vit_patch_stats")
+    with _Timed("gemm", M=B * n, N=D, K=Cc * 256, flags=EPI_LNFOLD | EPI_BIAS, flops=2.0 * B * n * D * Cc * 256):
+        rc = lib().b200vit_patch_embed_tma(_ptr(img), _ptr(w_perm), _ptr(bias), _ptr(col_s), _ptr(stats), float(eps),
+                                           _ptr(out_f32), out_f32.stride(0), B, Cc, H, W, D, _stream())
+    _check(rc, "b200vit_patch_embed_tma")
 
 
 def embed_tokens(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, cls: Optional[torch.Tensor],

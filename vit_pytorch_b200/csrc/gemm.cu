@@ -35,6 +35,16 @@ struct GemmParams {
   float ln_eps;
   const float* col_s;  // [N]
   float* stats_out;    // [M][2]
+  // Rows of A (and of the output) per tile: BLOCK_M, or -- patch mode -- the patches of `patch_ght` patch rows of one
+  // image (<= 128; the rest of the 128-row MMA tile is ignored).
+  int rows_per_tile;
+  // Patch mode (b200vit_patch_embed_tma): A is not a matrix in memory but the NCHW image itself, read through a 5-D
+  // tensor map (pixel 16 | pixel row 16 | patch column | patch row | image x channel).  k block kb = channel * 4 + g
+  // covers pixel rows 4g .. 4g+3 of every patch: one 128-byte shared-memory row per patch = a K-major operand row.
+  int patch;
+  int patch_ght;            // patch rows per tile
+  int patch_tiles_per_img;  // gh / patch_ght
+  int patch_C;              // channels
 };
 
 template <int BLOCK_N, int STAGES>
@@ -105,8 +115,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          if (p.patch) {
+            // im2col-free A tile: rows_per_tile patches x (4 pixel rows x 16 pixels) of channel kb / 4
+            const int img = m_blk / p.patch_tiles_per_img, tin = m_blk % p.patch_tiles_per_img;
+            mbar_arrive_expect_tx(&full_bar[stage], p.rows_per_tile * 128 + L::B_BYTES);
+            tma_load_5d(sa, &tmA, &full_bar[stage], 0, (kb & 3) * 4, 0, tin * p.patch_ght, img * p.patch_C + (kb >> 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
           if (++stage == STAGES) {
             stage = 0;
@@ -165,8 +182,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile % p.num_n_tiles;
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row = m_blk * p.rows_per_tile + quad * 32 + lane;
+      const bool row_ok = row < p.M && quad * 32 + lane < p.rows_per_tile;
       float mu = 0.f, rstd = 1.f;
       if ((flags & B200VIT_EPI_LNFOLD) && row_ok) {
         float s1 = 0.f, s2 = 0.f;
@@ -310,7 +327,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   using L = GemmSmem<BLOCK_N, STAGES>;
   auto kern = gemm_bf16_kernel<BLOCK_N, STAGES>;
   B200_ENSURE_SMEM(kern, L::DYN_BYTES);
-  p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  if (!p.patch) p.rows_per_tile = BLOCK_M;
+  p.num_m_tiles = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -425,4 +443,67 @@ extern "C" int b200vit_gemm_headnorm_bf16(const void* A, int64_t lda, const void
   if (rc) return rc;
   if (hln) return b200vit_layernorm_heads(out_bf16, ldo, head_gamma, M, norm_heads, dh, head_eps, stream);
   return b200vit_rmsnorm_heads(out_bf16, ldo, head_gamma, M, norm_heads, dh, stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// im2col-free patch embedding (north star: "stages p x p x 3 pixels through TMA into shared memory and feeds a tcgen05
+// GEMM"): the patch projection reads the NCHW image directly; Rearrange('b c (h p1) (w p2) -> b (h w) (p1 p2 c)') and
+// the LayerNorm over the patch (vit.py:100-101) never materialise.  LayerNorm is folded exactly like everywhere else:
+//   LN(x) W^T + b  =  rstd (x (gamma W)^T - mu colsum) + (W beta + b),
+// x = raw bf16 pixels (the A operand), (mu, rstd) from b200vit_patch_stats.  The K order of the operand is
+// (c, p1, p2) -- the image's own order -- so the caller permutes the weight's columns from the reference's (p1 p2 c).
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int b200vit_patch_embed_tma(const void* img, const void* w_perm, const float* bias, const float* col_s,
+                                       const float* patch_stats, float ln_eps, float* out_f32, int64_t ldo, int B, int C,
+                                       int H, int W, int D, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(img && w_perm && bias && col_s && patch_stats && out_f32, "patch_embed_tma: null pointer");
+  B200_CHECK_ARG(B > 0 && C > 0 && C <= 8 && H > 0 && W > 0 && (H % 16) == 0 && (W % 16) == 0,
+                 "patch_embed_tma: needs 16 x 16 patches on an image whose sides are multiples of 16 (got %dx%d)", H, W);
+  B200_CHECK_ARG(D > 0 && (D % 8) == 0 && ldo >= D, "patch_embed_tma: bad D=%d / ldo", D);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_perm) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(col_s) & 15) == 0,
+                 "patch_embed_tma: pointers must be 16-byte aligned");
+  const int gh = H / 16, gw = W / 16;
+  B200_CHECK_ARG(gw <= 128, "patch_embed_tma: %d patches per row do not fit a 128-row tile", gw);
+  int ght = 1;  // largest divisor of gh whose patch rows fit the 128-row MMA tile
+  for (int d = 1; d <= gh; ++d)
+    if (gh % d == 0 && d * gw <= 128) ght = d;
+  const int K = C * 256;
+  GemmParams p{};
+  p.M = B * gh * gw; p.N = D; p.K = K;
+  p.flags = B200VIT_EPI_LNFOLD | B200VIT_EPI_BIAS;
+  p.out_f32 = out_f32;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.ln_sums = patch_stats;
+  p.ln_parts = 1;
+  p.stats_parts = b200vit_stats_parts(D);
+  p.ln_inv_dim = 1.0f / (float)K;
+  p.ln_eps = ln_eps;
+  p.col_s = col_s;
+  p.patch = 1;
+  p.patch_ght = ght;
+  p.patch_tiles_per_img = gh / ght;
+  p.patch_C = C;
+  p.rows_per_tile = ght * gw;
+  CUtensorMap tmA, tmB;
+  {
+    // innermost first: pixel in a patch row | pixel row in the patch | patch column | patch row | image x channel
+    const uint64_t dims[5] = {16, 16, (uint64_t)gw, (uint64_t)gh, (uint64_t)B * C};
+    const uint64_t strides[4] = {(uint64_t)W * 2, 32, (uint64_t)16 * W * 2, (uint64_t)H * W * 2};
+    const uint32_t box[5] = {16, 4, (uint32_t)gw, (uint32_t)ght, 1};
+    int rc = encode_tmap_bf16(&tmA, img, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)D};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, 256};
+    int rc = encode_tmap_bf16(&tmB, w_perm, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch_gemm<256, 4>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -953,3 +953,54 @@ extern "C" int b200vit_patchify_varlen_ln(const int64_t* img_ptrs_dev, const int
   b200::count_launch();
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// (sum, sum of squares) of the C x 16 x 16 bf16 pixels of every 16 x 16 patch: the LayerNorm statistics the TMA patch
+// embedding folds into its epilogue (b200vit_patch_embed_tma).  One warp per patch; lane = pixel row of the patch
+// (channel-major), 32 bytes per lane and row.
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+__global__ void __launch_bounds__(256)
+patch_stats_kernel(const __nv_bfloat16* __restrict__ img, float* __restrict__ stats, long long num_patches, int C,
+                   int H, int W) {
+  const long long pidx = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pidx >= num_patches) return;
+  const int gw = W / 16, gh = H / 16;
+  const int pw = (int)(pidx % gw), ph = (int)((pidx / gw) % gh);
+  const long long b = pidx / ((long long)gw * gh);
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = lane; r < C * 16; r += 32) {
+    const int c = r >> 4, p1 = r & 15;
+    const uint4* src = reinterpret_cast<const uint4*>(img + ((b * C + c) * H + ph * 16 + p1) * (long long)W + pw * 16);
+    const uint4 v0 = src[0], v1 = src[1];
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+      s1 += lo + hi;
+      s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    stats[2 * pidx] = s1;
+    stats[2 * pidx + 1] = s2;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200vit_patch_stats(const void* img, float* stats, int B, int C, int H, int W, void* stream) {
+  B200_CHECK_ARG(img && stats, "patch_stats: null pointer");
+  B200_CHECK_ARG(B > 0 && C > 0 && (H % 16) == 0 && (W % 16) == 0 && H > 0 && W > 0,
+                 "patch_stats: needs 16 x 16 patches on an image whose sides are multiples of 16");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0, "patch_stats: image must be 16-byte aligned");
+  const long long np = (long long)B * (H / 16) * (W / 16);
+  b200::patch_stats_kernel<<<(unsigned)((np + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(img), stats, np, C, H, W);
+  B200_CHECK_CUDA(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}

@@ -25,6 +25,7 @@ from . import _lib
 
 _FORCE_EAGER_ENV = "B200VIT_DISABLE_FUSED"
 _LN_MODE_ENV = "B200VIT_LN_MODE"      # "fold" (default) | "exact"
+_PATCH_MODE_ENV = "B200VIT_PATCH_MODE"  # "tma" (default: im2col-free 16x16 patch embedding) | "gather"
 
 
 def ln_mode() -> str:
@@ -358,6 +359,16 @@ class PatchEmbedEngine:
             "ln2.w": _f32(ln2.weight), "ln2.b": _f32(ln2.bias),
         }
         t["kp"] = kp  # type: ignore[assignment]
+        ph, pw = o.patch_size
+        if ph == 16 and pw == 16 and pd % 256 == 0:
+            # im2col-free path (b200vit_patch_embed_tma): LayerNorm(patch) folded into the projection, weight columns
+            # permuted from the reference's (p1 p2 c) order (vit.py:100) to the image's own (c p1 p2)
+            C = pd // 256
+            w32 = lin.weight.detach().float()
+            wg = w32 * ln1.weight.detach().float()[None, :]
+            t["tma.w"] = wg.view(-1, 256, C).permute(0, 2, 1).reshape(-1, pd).to(torch.bfloat16).contiguous()
+            t["tma.s"] = t["tma.w"].float().sum(dim=1).contiguous()           # from the ROUNDED weights the MMA sees
+            t["tma.b"] = (w32 @ ln1.bias.detach().float() + lin.bias.detach().float()).contiguous()
         cls = getattr(o, "cls_token", None)
         t["cls"] = _f32(cls) if (cls is not None and cls.shape[0] > 0) else None
         reg = getattr(o, "register_tokens", None)          # simple_vit_with_register_tokens.py:103,124-126
@@ -396,10 +407,16 @@ class PatchEmbedEngine:
         if pos.shape[0] < n + ncls:
             raise ValueError(f"sequence of {n + ncls} tokens exceeds the positional table ({pos.shape[0]})")
         dev = img.device
-        a0 = torch.empty(B * n, t["kp"], device=dev, dtype=torch.bfloat16)
-        _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw, eps=o.to_patch_embedding[1].eps)
         y = torch.empty(B * n, D, device=dev, dtype=torch.float32)
-        _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
+        if "tma.w" in t and os.environ.get(_PATCH_MODE_ENV, "tma") == "tma" and W // pw <= 128 and D % 8 == 0:
+            # the tcgen05 GEMM reads the image itself: no patch matrix, no LayerNorm pass
+            stats_p = torch.empty(B * n, 2, device=dev, dtype=torch.float32)
+            _lib.patch_embed_tma(img.contiguous(), t["tma.w"], t["tma.b"], t["tma.s"], stats_p, y,
+                                 eps=o.to_patch_embedding[1].eps)
+        else:
+            a0 = torch.empty(B * n, t["kp"], device=dev, dtype=torch.bfloat16)
+            _lib.patchify_ln(img.contiguous(), t["ln1.w"], t["ln1.b"], a0, ph, pw, eps=o.to_patch_embedding[1].eps)
+            _lib.gemm(a0, t["w"], out_f32=y, bias=t["b"])
         x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
         _lib.embed_tokens(y, t["ln2.w"], t["ln2.b"], t["cls"], pos, x, B, n, ncls, xb=xb, stats=stats,
                           eps=o.to_patch_embedding[3].eps, tail=t["tail"])
