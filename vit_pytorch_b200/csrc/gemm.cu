@@ -39,17 +39,22 @@ struct GemmParams {
   // image (<= 128; the rest of the 128-row MMA tile is ignored).
   int rows_per_tile;
   // Patch mode (b200vit_patch_embed_tma): A is not a matrix in memory but the NCHW image itself, read through a 5-D
-  // tensor map (pixel 16 | pixel row 16 | patch column | patch row | image x channel).  k block kb = channel * 4 + g
-  // covers pixel rows 4g .. 4g+3 of every patch: one 128-byte shared-memory row per patch = a K-major operand row.
+  // tensor map (pixel 16 | patch column | patch row | pixel row 16 | image x channel).  k block kb = channel * 4 + g
+  // covers pixel rows 4g .. 4g+3 of every patch.  With a swizzled tensor map every box row (16 pixels = 32 bytes)
+  // lands on its own 128-byte shared-memory row (measured: tools/patch_tma_probe.py), so the four pixel rows of a
+  // k block cannot share one operand row; they are loaded as four boxes into four 16 KB slabs, each a K-major
+  // operand of which the tensor core reads the first 16 k (one tcgen05.mma k-step per slab).
   int patch;
   int patch_ght;            // patch rows per tile
   int patch_tiles_per_img;  // gh / patch_ght
   int patch_C;              // channels
 };
 
-template <int BLOCK_N, int STAGES>
+// PATCH: the A stage holds FOUR 16 KB slabs, one per 16-wide k-step (see GemmParams::patch).
+template <int BLOCK_N, int STAGES, bool PATCH = false>
 struct GemmSmem {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_SLAB = BLOCK_M * BLOCK_K * 2;
+  static constexpr int A_BYTES = PATCH ? 4 * A_SLAB : A_SLAB;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
@@ -58,11 +63,11 @@ struct GemmSmem {
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool PATCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using L = GemmSmem<BLOCK_N, STAGES>;
+  using L = GemmSmem<BLOCK_N, STAGES, PATCH>;
   constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256 (power of two)
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "TMEM columns must be a power of two");
 
@@ -115,11 +120,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          if (p.patch) {
+          if (PATCH) {
             // im2col-free A tile: rows_per_tile patches x (4 pixel rows x 16 pixels) of channel kb / 4
             const int img = m_blk / p.patch_tiles_per_img, tin = m_blk % p.patch_tiles_per_img;
             mbar_arrive_expect_tx(&full_bar[stage], p.rows_per_tile * 128 + L::B_BYTES);
-            tma_load_5d(sa, &tmA, &full_bar[stage], 0, (kb & 3) * 4, 0, tin * p.patch_ght, img * p.patch_C + (kb >> 2));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              tma_load_5d(sa + j * L::A_SLAB, &tmA, &full_bar[stage], 0, 0, tin * p.patch_ght, (kb & 3) * 4 + j,
+                          img * p.patch_C + (kb >> 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
@@ -154,7 +162,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            // (patch mode: the k-th 16 k of A are the first 32 bytes of the rows of slab k)
+            const uint64_t ad = PATCH ? make_smem_desc_sw128(sa + k * L::A_SLAB, 16, 1024) : adesc + 2 * k;
+            umma_ss(d_tmem, ad, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) {
@@ -322,10 +332,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool PATCH = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
-  using L = GemmSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, STAGES>;
+  using L = GemmSmem<BLOCK_N, STAGES, PATCH>;
+  static_assert(L::DYN_BYTES <= 227 * 1024, "gemm: shared memory budget");
+  auto kern = gemm_bf16_kernel<BLOCK_N, STAGES, PATCH>;
   B200_ENSURE_SMEM(kern, L::DYN_BYTES);
   if (!p.patch) p.rows_per_tile = BLOCK_M;
   p.num_m_tiles = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
@@ -491,10 +502,10 @@ extern "C" int b200vit_patch_embed_tma(const void* img, const void* w_perm, cons
   p.rows_per_tile = ght * gw;
   CUtensorMap tmA, tmB;
   {
-    // innermost first: pixel in a patch row | pixel row in the patch | patch column | patch row | image x channel
-    const uint64_t dims[5] = {16, 16, (uint64_t)gw, (uint64_t)gh, (uint64_t)B * C};
-    const uint64_t strides[4] = {(uint64_t)W * 2, 32, (uint64_t)16 * W * 2, (uint64_t)H * W * 2};
-    const uint32_t box[5] = {16, 4, (uint32_t)gw, (uint32_t)ght, 1};
+    // innermost first: pixel in a patch row | patch column | patch row | pixel row in the patch | image x channel
+    const uint64_t dims[5] = {16, (uint64_t)gw, (uint64_t)gh, 16, (uint64_t)B * C};
+    const uint64_t strides[4] = {32, (uint64_t)16 * W * 2, (uint64_t)W * 2, (uint64_t)H * W * 2};
+    const uint32_t box[5] = {16, (uint32_t)gw, (uint32_t)ght, 1, 1};
     int rc = encode_tmap_bf16(&tmA, img, 5, dims, strides, box);
     if (rc) return rc;
   }
@@ -505,5 +516,5 @@ extern "C" int b200vit_patch_embed_tma(const void* img, const void* w_perm, cons
     int rc = encode_tmap_bf16(&tmB, w_perm, 2, dims, strides, box);
     if (rc) return rc;
   }
-  return launch_gemm<256, 4>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 2, true>(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
 }
