@@ -271,7 +271,20 @@ def run_reference_arm(args, rank: int, world: int) -> None:
     torch.set_num_threads(cores)
     sb = args.cpu_batch
     fn, kind = cpu_reference_runner(args.model, cfg, sb, torch.bfloat16)
-    sec = time_cpu(fn, args.steps, max(1, min(args.warmup, 2)) if args.warmup > 0 else 0)
+    nwarm = max(1, min(args.warmup, 2)) if args.warmup > 0 else 0
+    # bounded sample: the whole --steps/--warmup run has to end within a few minutes on whatever host this is (the
+    # protocol fixes threads = all cores, where a 16-image forward can take seconds): halve the sample until the
+    # estimate from one probe forward fits args.cpu_budget seconds
+    with torch.inference_mode():
+        fn()
+        while sb > 1:
+            t0 = time.perf_counter(); fn(); probe = time.perf_counter() - t0
+            if probe * (args.steps + nwarm) <= args.cpu_budget:
+                break
+            sb = max(1, sb // 2)
+            fn, kind = cpu_reference_runner(args.model, cfg, sb, torch.bfloat16)
+            fn()
+    sec = time_cpu(fn, args.steps, nwarm)
     val = sb / sec
     matrix = None if args.no_matrix else cpu_matrix(args.model, cfg, args.matrix_budget)
     src = "baseline/_ref/vit_pytorch (unmodified lucidrains/vit-pytorch 1.23.6)" if kind == "reference" \
@@ -604,7 +617,9 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
     ap.add_argument("--no-matrix", action="store_true", help="reference arm: skip the fp32/bf16 x B=16/64 matrix")
-    ap.add_argument("--matrix-budget", type=float, default=90.0, help="seconds the reference arm may spend on the matrix")
+    ap.add_argument("--matrix-budget", type=float, default=60.0, help="seconds the reference arm may spend on the matrix")
+    ap.add_argument("--cpu-budget", type=float, default=120.0,
+                    help="reference arm: seconds the timed steps may take; the per-step sample is halved until they fit")
     ap.add_argument("--model", default="vit_b16", choices=sorted(MODELS), help="vit_b16 is the headline config")
     ap.add_argument("--dim-head", type=int, default=64, help="ViT-H/14 canonical is 80")
     args = ap.parse_args()
