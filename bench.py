@@ -398,6 +398,19 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # ---- per-rank compute without the collective (N > 1): which GPU sets the pace of the coupled step ----
+    per_rank_compute_ms = None
+    if world > 1:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            with torch.inference_mode():
+                model(img)
+        e1.record()
+        torch.cuda.synchronize()
+        per_rank_compute_ms = [m / args.steps for m in all_ranks(e0.elapsed_time(e1))]
+        sync_all()
+
     # ---- the collective on its own (N > 1): CUDA events around `steps` all-gathers of the logits ----
     allgather_ms = None
     if world > 1:
@@ -561,7 +574,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         "frac_of_bf16_burst_peak": tf / float(peaks["bf16_tflops"]),
         "frac_of_bf16_sustained_peak": tf / peak,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "joules_per_image": energy,
-        "per_rank_ms_per_step": [m / args.steps for m in per_rank_ms], "allgather_ms": allgather_ms,
+        "per_rank_ms_per_step": [m / args.steps for m in per_rank_ms],
+        "per_rank_compute_ms": per_rank_compute_ms, "allgather_ms": allgather_ms,
         "roofline": roofline, "roofline_attention": roofline_attention,
         "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "breakdown": breakdown,
     }
