@@ -204,3 +204,21 @@ def test_missing_library_raises_on_eligible_input(monkeypatch, tmp_path):
     with pytest.raises(_lib.B200VitError):
         with torch.inference_mode():
             m(g["input"].to(DEV))
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """vit_pytorch_b200.graph.GraphedForward: every library launch lands in the capture stream; replays on new inputs
+    reproduce the call-by-call fused forward bit for bit."""
+    from vit_pytorch_b200.graph import GraphedForward
+    torch.manual_seed(0)
+    m = ViT(image_size=64, patch_size=16, num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256).eval()
+    m = m.to(DEV, torch.bfloat16)
+    a = torch.randn(4, 3, 64, 64, device=DEV).bfloat16()
+    b = torch.randn(4, 3, 64, 64, device=DEV).bfloat16()
+    with torch.inference_mode():
+        ya, yb = m(a).clone(), m(b).clone()
+        g = GraphedForward(m, a)
+        assert torch.equal(g(b), yb)
+        assert torch.equal(g(a), ya)
+    with pytest.raises(ValueError):
+        g(a[:2])
