@@ -12,6 +12,9 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = ["simplevit_tiny", "vit_tiny_cls", "vit_tiny_mean_nonsquare", "vit_tiny_tokens"]
 REFERENCE_DIR = os.environ.get("VIT_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_DIR, "vit_pytorch")):
+    # GPU box: the unmodified reference installed under baseline/_ref travels with the snapshot
+    REFERENCE_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def pytest_configure(config):

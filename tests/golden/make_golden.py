@@ -66,6 +66,20 @@ CASES2 = {
 }
 
 
+# Round 2, later: the 1-D / 3-D front-ends of SURVEY.md 8(f3) (series and video inputs; `img` = the non-channel dims)
+CASES3 = {
+    "simplevit_1d": dict(kind="simple_vit_1d", seed=12, batch=3, img=(256,),
+                         kwargs=dict(seq_len=256, patch_size=16, num_classes=10, dim=128, depth=2, heads=2,
+                                     mlp_dim=256)),
+    "simplevit_3d": dict(kind="simple_vit_3d", seed=13, batch=2, img=(4, 32, 24),
+                         kwargs=dict(image_size=(32, 24), image_patch_size=8, frames=4, frame_patch_size=2,
+                                     num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256)),
+    "simplevit_3d_pf1": dict(kind="simple_vit_3d", seed=14, batch=2, img=(3, 32, 48),
+                             kwargs=dict(image_size=(32, 48), image_patch_size=16, frames=3, frame_patch_size=1,
+                                         num_classes=10, dim=192, depth=2, heads=3, mlp_dim=384)),
+}
+
+
 def reference_class(kind: str):
     """kind -> class of the UNMODIFIED reference."""
     import importlib
@@ -213,11 +227,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "navit_config5":
         make_navit_config5()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "frontends":
+        for n, s in CASES3.items():
+            make(n, s)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "round2":
         for n, s in CASES2.items():
             make(n, s)
         sys.exit(0)
-    for n, s in {**CASES, **CASES2}.items():
+    for n, s in {**CASES, **CASES2, **CASES3}.items():
         make(n, s)
     make_navit()
     make_navit_config5()

@@ -147,3 +147,90 @@ def test_reference_wrappers_accept_the_dropin():
     v = ViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=2, heads=2, mlp_dim=48, dim_head=16).eval()
     logits, emb = Extractor(v)(torch.randn(2, 3, 32, 32))
     assert logits.shape == (2, 3) and emb.shape == (2, 17, 32)
+
+
+def _pair_with_reference(**kwargs):
+    """Our ViT and the reference's with the same weights (fp32, eval)."""
+    import importlib
+    import_reference()
+    RefViT = importlib.import_module("vit_pytorch.vit").ViT
+    torch.manual_seed(0)
+    ours = ViT(**kwargs).eval()
+    ref = RefViT(**kwargs).eval()
+    ref.load_state_dict(ours.state_dict())
+    return ours, ref
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+def test_reference_mae_wrapper_runs_on_the_dropin():
+    """MAE (reference mae.py:28-31,50-55,74) reads `to_patch_embedding[0]`, `[1:]`, `[2].weight`, `pos_embedding`,
+    `pool` and calls `encoder.transformer(tokens)` on the unmasked quarter of the tokens: same loss as on the
+    reference's own ViT.  (pool='mean': with the 2-D `pos_embedding` of vit.py:107 the wrapper's `[:, 1:n+1]` slice for
+    pool='cls' -- and SimMIM's, simmim.py:45 -- fails on the reference's own ViT too, so there is nothing to match.)"""
+    import importlib
+    ours, ref = _pair_with_reference(image_size=32, patch_size=8, num_classes=5, dim=64, depth=2, heads=2, mlp_dim=96,
+                                     pool="mean")
+    MAE = importlib.import_module("vit_pytorch.mae").MAE
+    make = lambda enc: MAE(encoder=enc, decoder_dim=32, masking_ratio=0.75, decoder_depth=1, decoder_heads=2,  # noqa
+                           decoder_dim_head=16)
+    torch.manual_seed(1)
+    a = make(ours).eval()
+    b = make(ref).eval()
+    b.load_state_dict(a.state_dict())
+    img = torch.randn(3, 3, 32, 32)
+    with torch.no_grad():
+        torch.manual_seed(2)
+        la = a(img)
+        torch.manual_seed(2)
+        lb = b(img)
+    assert torch.allclose(la, lb, rtol=1e-5, atol=1e-6), (la, lb)
+    a(img).backward()                                # and it trains: gradients reach the encoder through the wrapper
+    assert ours.transformer.layers[0][0].to_qkv.weight.grad is not None
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+def test_reference_distill_wrapper_accepts_the_dropin_as_teacher():
+    """DistillWrapper (reference distill.py:104-152) calls `teacher(img)` under no_grad."""
+    import importlib
+    import_reference()
+    distill = importlib.import_module("vit_pytorch.distill")
+    kw = dict(image_size=32, patch_size=8, num_classes=5, dim=64, depth=1, heads=2, mlp_dim=96)
+    torch.manual_seed(0)
+    teacher = ViT(**kw).eval()
+    student = distill.DistillableViT(**kw)
+    loss = distill.DistillWrapper(student=student, teacher=teacher, temperature=3, alpha=0.5)(
+        torch.randn(2, 3, 32, 32), torch.tensor([1, 3]))
+    assert loss.dim() == 0 and torch.isfinite(loss)
+
+
+def test_recorder_and_extractor_twins():
+    """vit_pytorch_b200.recorder / .extractor mirror reference recorder.py:10-59 / extractor.py:18-92."""
+    from vit_pytorch_b200.extractor import Extractor
+    from vit_pytorch_b200.recorder import Recorder
+    torch.manual_seed(0)
+    v = ViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=2, heads=2, mlp_dim=48, dim_head=16).eval()
+    img = torch.randn(2, 3, 32, 32)
+    with torch.no_grad():
+        plain = v(img)
+        rec = Recorder(v)
+        pred, attns = rec(img)
+        assert attns.shape == (2, 2, 2, 17, 17) and torch.allclose(attns.sum(-1), torch.ones(2, 2, 2, 17), atol=1e-5)
+        assert torch.equal(pred, plain)
+        assert rec.eject() is v and not any(l[0].attend._forward_hooks for l in v.transformer.layers)
+        ext = Extractor(v)
+        pred, emb = ext(img)
+        assert torch.equal(pred, plain) and emb.shape == (2, 17, 32)
+        assert ext(img, return_embeddings_only=True).shape == (2, 17, 32)
+        first = Extractor(v, layer=v.transformer.layers[0][1], layer_save_input=True)
+        _, inp = first(img)
+        assert isinstance(inp, tuple) and inp[0].shape == (2, 17, 32)
+    if reference_available():
+        import importlib
+        import_reference()
+        RefRecorder = importlib.import_module("vit_pytorch.recorder").Recorder
+        RefViT = importlib.import_module("vit_pytorch.vit").ViT
+        r = RefViT(image_size=32, patch_size=8, num_classes=3, dim=32, depth=2, heads=2, mlp_dim=48, dim_head=16).eval()
+        r.load_state_dict(v.state_dict())
+        with torch.no_grad():
+            _, ref_attns = RefRecorder(r)(img)
+        assert torch.allclose(ref_attns, attns, atol=1e-6)

@@ -222,3 +222,48 @@ def test_cuda_graph_replay_is_bit_identical():
         assert torch.equal(g(a), ya)
     with pytest.raises(ValueError):
         g(a[:2])
+
+
+@pytest.mark.parametrize("kind", ["vit_cls", "vit_mean", "simple"])
+def test_extractor_hook_keeps_the_fused_path(kind):
+    """Extractor (reference extractor.py:50-59) hooks `vit.transformer`: the fused forward routes the tokens through
+    that module call, so the hook sees the encoder output while every block still runs in the sm_100a kernels."""
+    from vit_pytorch_b200.extractor import Extractor
+    torch.manual_seed(0)
+    kw = dict(image_size=64, patch_size=8, num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256)
+    m = (SimpleViT(**kw) if kind == "simple" else ViT(pool="mean" if kind == "vit_mean" else "cls", **kw)).eval()
+    m = m.to(DEV, torch.bfloat16)
+    img = torch.randn(3, 3, 64, 64, device=DEV).bfloat16()
+    with torch.inference_mode():
+        plain = m(img)
+        ext = Extractor(m)
+        assert m.fused_reason(img) is None
+        _lib.reset_launch_count()
+        pred, emb = ext(img)
+        assert _lib.launch_count() >= 3 + 5 * 2
+        n = 64 + (0 if kind == "simple" else 1)
+        assert emb.shape == (3, n, 128) and emb.dtype == torch.bfloat16
+        assert (pred.float() - plain.float()).abs().max() < 2e-2          # tokens passed through bf16 once
+        ext.eject()
+        ref_emb = {}
+        h = m.transformer.register_forward_hook(lambda _m, _i, o: ref_emb.setdefault("o", o))
+        m.float().forward_eager(img.float())
+        h.remove()
+    assert (emb.float() - ref_emb["o"]).abs().max() < 6e-2 and (emb.float() - ref_emb["o"]).abs().mean() < 6e-3
+
+
+def test_hook_inside_the_transformer_still_forces_the_pytorch_graph():
+    from vit_pytorch_b200.recorder import Recorder
+    torch.manual_seed(0)
+    m = ViT(image_size=32, patch_size=8, num_classes=4, dim=128, depth=2, heads=2, mlp_dim=256).eval()
+    m = m.to(DEV, torch.bfloat16)
+    img = torch.randn(2, 3, 32, 32, device=DEV).bfloat16()
+    rec = Recorder(m)
+    with torch.inference_mode():
+        _lib.reset_launch_count()
+        pred, attns = rec(img)
+        assert _lib.launch_count() == 0 and "hooks" in m.fused_reason(img)
+        assert attns.shape == (2, 2, 2, 17, 17)
+        rec.eject()
+        assert m.fused_reason(img) is None
+        assert (m(img).float() - pred.float()).abs().max() < 3e-2

@@ -10,7 +10,8 @@ from vit_pytorch_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-ALL = ["vit_tiny_noproj", "simplevit_registers", "simplevit_qknorm", "simplevit_patchdrop", "simplevit_flash"]
+ALL = ["vit_tiny_noproj", "simplevit_registers", "simplevit_qknorm", "simplevit_patchdrop", "simplevit_flash",
+       "simplevit_1d", "simplevit_3d", "simplevit_3d_pf1"]
 
 
 def dropin_class(kind: str):
@@ -117,3 +118,35 @@ def test_gemm_head_layernorm_epilogue(M):
     assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2)
     # the v third is the plain projection (accumulation order differs from torch's: compare within a bf16 ulp)
     assert torch.allclose(out[:, 2 * H * 64:].float(), y[:, 2 * H * 64:], rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("pf", [1, 2, 4])
+def test_video_front_end_matches_its_own_pytorch_graph(pf):
+    """simple_vit_3d on a larger clip: the (pf p1 p2 c) boxes reach the 2-D patch kernels as a (B, C, F*H, W) image
+    (frame_patch_size 1 with 16 x 16 boxes: the TMA patch embedding); compared with the module's own fp32 graph."""
+    from vit_pytorch_b200.simple_vit_3d import SimpleViT
+    torch.manual_seed(2)
+    m = SimpleViT(image_size=(64, 48), image_patch_size=16, frames=8, frame_patch_size=pf, num_classes=9, dim=192,
+                  depth=2, heads=3, mlp_dim=384).eval().to(DEV, torch.bfloat16)
+    video = torch.randn(3, 3, 8, 64, 48, device=DEV).bfloat16()
+    _lib.reset_launch_count()
+    with torch.inference_mode():
+        assert m.fused_reason(video) is None, m.fused_reason(video)
+        fused = m(video)
+        assert _lib.launch_count() > 0
+        eager = m.float().forward_eager(video.float())
+    assert fused.shape == (3, 9)
+    assert (fused.float() - eager).abs().max() < 2e-2
+
+
+def test_series_front_end_matches_its_own_pytorch_graph():
+    from vit_pytorch_b200.simple_vit_1d import SimpleViT
+    torch.manual_seed(3)
+    m = SimpleViT(seq_len=4096, patch_size=8, num_classes=5, dim=128, depth=2, heads=2, mlp_dim=256, channels=6)
+    m = m.eval().to(DEV, torch.bfloat16)
+    series = torch.randn(2, 6, 4096, device=DEV).bfloat16()
+    with torch.inference_mode():
+        assert m.fused_reason(series) is None, m.fused_reason(series)
+        fused = m(series)
+        eager = m.float().forward_eager(series.float())
+    assert (fused.float() - eager).abs().max() < 2e-2

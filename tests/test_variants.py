@@ -9,7 +9,8 @@ import torch
 
 from conftest import import_reference, load_golden, reference_available
 
-VARIANTS = ["simplevit_registers", "simplevit_qknorm", "simplevit_patchdrop", "simplevit_flash"]
+VARIANTS = ["simplevit_registers", "simplevit_qknorm", "simplevit_patchdrop", "simplevit_flash",
+            "simplevit_1d", "simplevit_3d", "simplevit_3d_pf1"]
 ALL = ["vit_tiny_noproj"] + VARIANTS
 
 

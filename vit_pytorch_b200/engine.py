@@ -71,6 +71,20 @@ def hooks_inside(root: nn.Module, skip: Tuple[nn.Module, ...] = ()) -> bool:
     return False
 
 
+def transformer_is_hooked(owner: nn.Module) -> bool:
+    """A hook on the Transformer module ITSELF (reference extractor.py:50-59 registers one to read the embeddings):
+    the fused forward then passes the tokens through `owner.transformer(...)` as a module call, so the hook fires
+    with the real input / output while the blocks still run fused (hooks strictly inside it need the eager graph)."""
+    return _has_hooks(owner.transformer)
+
+
+def hooked_transformer_tokens(owner: nn.Module, x: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """x fp32 [B*N, D] (assembled tokens) -> owner.transformer(tokens bf16 [B, N, D]) through Module.__call__."""
+    tok = torch.empty(B * N, x.shape[1], device=x.device, dtype=torch.bfloat16)
+    _lib.cast_f32_bf16(x.view(-1), tok.view(-1))
+    return owner.transformer(tok.view(B, N, x.shape[1]))
+
+
 def why_not_fused(params: List[torch.Tensor], x: torch.Tensor, *, training: bool, dropout_p: float) -> Optional[str]:
     """None if the fused path applies to this call, else the reason the eager PyTorch graph is used."""
     if os.environ.get(_FORCE_EAGER_ENV, "0") == "1":
@@ -359,7 +373,7 @@ class PatchEmbedEngine:
             "ln2.w": _f32(ln2.weight), "ln2.b": _f32(ln2.bias),
         }
         t["kp"] = kp  # type: ignore[assignment]
-        ph, pw = o.patch_size
+        ph, pw = getattr(o, "fused_patch_box", None) or o.patch_size
         if ph == 16 and pw == 16 and pd % 256 == 0:
             # im2col-free path (b200vit_patch_embed_tma): LayerNorm(patch) folded into the projection, weight columns
             # permuted from the reference's (p1 p2 c) order (vit.py:100) to the image's own (c p1 p2)
@@ -389,11 +403,14 @@ class PatchEmbedEngine:
             cache[key] = self.owner.fused_pos_table(gh, gw).to(device=device, dtype=torch.float32).contiguous()
         return cache[key]
 
-    def run(self, img: torch.Tensor, xb: Optional[torch.Tensor] = None,
-            stats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:
-        """img [B, C, H, W] bf16 -> (x fp32 [B*N, D], B, N); optionally also the bf16 copy of x and its row sums."""
+    def run(self, img: torch.Tensor, xb: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+            patch: Optional[Tuple[int, int]] = None, pos: Optional[torch.Tensor] = None
+            ) -> Tuple[torch.Tensor, int, int]:
+        """img [B, C, H, W] bf16 -> (x fp32 [B*N, D], B, N); optionally also the bf16 copy of x and its row sums.
+        `patch` / `pos` override the owner's patch size and positional table: the 1-D and 3-D front-ends
+        (simple_vit_1d.py, simple_vit_3d.py) present their input as a [B, C, H', W'] view with its own patch box."""
         o = self.owner
-        ph, pw = o.patch_size
+        ph, pw = patch if patch is not None else o.patch_size
         B, C, H, W = img.shape
         if H % ph or W % pw:
             raise ValueError("Image dimensions must be divisible by the patch size.")
@@ -403,12 +420,14 @@ class PatchEmbedEngine:
         ntail = 0 if t["tail"] is None else t["tail"].shape[0]
         N = n + ncls + ntail
         D = t["w"].shape[0]
-        pos = self._pos_table(t, H // ph, W // pw, img.device)
+        if pos is None:
+            pos = self._pos_table(t, H // ph, W // pw, img.device)
         if pos.shape[0] < n + ncls:
             raise ValueError(f"sequence of {n + ncls} tokens exceeds the positional table ({pos.shape[0]})")
         dev = img.device
         y = torch.empty(B * n, D, device=dev, dtype=torch.float32)
-        if "tma.w" in t and os.environ.get(_PATCH_MODE_ENV, "tma") == "tma" and W // pw <= 128 and D % 8 == 0:
+        if ("tma.w" in t and (ph, pw) == (16, 16) and os.environ.get(_PATCH_MODE_ENV, "tma") == "tma"
+                and W // pw <= 128 and D % 8 == 0):
             # the tcgen05 GEMM reads the image itself: no patch matrix, no LayerNorm pass
             stats_p = torch.empty(B * n, 2, device=dev, dtype=torch.float32)
             _lib.patch_embed_tma(img.contiguous(), t["tma.w"], t["tma.b"], t["tma.s"], stats_p, y,
@@ -422,9 +441,9 @@ class PatchEmbedEngine:
                           eps=o.to_patch_embedding[3].eps, tail=t["tail"])
         return x, B, N
 
-    def geometry(self, img: torch.Tensor) -> Tuple[int, int]:
+    def geometry(self, img: torch.Tensor, patch: Optional[Tuple[int, int]] = None) -> Tuple[int, int]:
         """(B, N) the image batch will produce, without running anything."""
-        ph, pw = self.owner.patch_size
+        ph, pw = patch if patch is not None else self.owner.patch_size
         cls = getattr(self.owner, "cls_token", None)
         reg = getattr(self.owner, "register_tokens", None)
         extra = (cls.shape[0] if cls is not None else 0) + (reg.shape[0] if reg is not None else 0)
@@ -454,7 +473,9 @@ class HeadEngine:
         return out
 
 
-def fused_mean_pooled_features(owner: nn.Module, img: torch.Tensor, pool_tokens: Optional[int] = None) -> torch.Tensor:
+def fused_mean_pooled_features(owner: nn.Module, img: torch.Tensor, pool_tokens: Optional[int] = None,
+                               patch: Optional[Tuple[int, int]] = None,
+                               pos: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Shared body of the SimpleViT-family fused forwards (reference simple_vit.py:110-117 and its variants):
     patch embedding (+ register tokens) -> encoder blocks -> final LayerNorm if the Transformer has one -> mean over
     the first `pool_tokens` tokens of every image (all tokens by default).  Returns fp32 [B, D]; must run inside
@@ -462,10 +483,17 @@ def fused_mean_pooled_features(owner: nn.Module, img: torch.Tensor, pool_tokens:
     if getattr(owner, "_patch_engine", None) is None:
         owner._patch_engine = PatchEmbedEngine(owner)
     eng = owner.transformer.engine()
-    B, N = owner._patch_engine.geometry(img)
+    B, N = owner._patch_engine.geometry(img, patch)
+    if transformer_is_hooked(owner):
+        x, B, N = owner._patch_engine.run(img, patch=patch, pos=pos)
+        xf = hooked_transformer_tokens(owner, x, B, N).reshape(B * N, -1).float()
+        pm = torch.empty(B, xf.shape[1], device=img.device, dtype=torch.float32)
+        _lib.mean_pool(xf, pm, B, N, xf.shape[1], n_pool=pool_tokens)
+        return pm
     primed = ln_mode() == "fold"
     ws = eng.workspace(B * N, img.device) if primed else None
-    x, B, N = owner._patch_engine.run(img, xb=ws["xn"] if primed else None, stats=ws["stats_in"] if primed else None)
+    x, B, N = owner._patch_engine.run(img, xb=ws["xn"] if primed else None, stats=ws["stats_in"] if primed else None,
+                                      patch=patch, pos=pos)
     D = x.shape[1]
     eng.run_blocks(x, B, N, primed=primed)
     if eng.has_final_norm():

@@ -14,8 +14,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode,
-                     on_device, why_not_fused)
+from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, fused_mean_pooled_features,
+                     hooks_inside, ln_mode, on_device, transformer_is_hooked, why_not_fused)
 from .vit import Patchify, pair
 
 
@@ -153,7 +153,7 @@ class SimpleViT(FusedWeightsMixin, nn.Module):
         if len(self.transformer.layers) == 0:
             return "depth == 0"
         r = why_not_fused(list(self.parameters()), img, training=self.training, dropout_p=0.0)
-        if r is None and hooks_inside(self, skip=(self.to_latent,)):
+        if r is None and hooks_inside(self, skip=(self.to_latent, self.transformer)):
             r = "forward hooks registered inside the model"
         if r is None:
             ph, pw = self.patch_size
@@ -182,18 +182,22 @@ class SimpleViT(FusedWeightsMixin, nn.Module):
         if self._patch_engine is None:
             self._patch_engine = PatchEmbedEngine(self)
         eng = self.transformer.engine()
-        B, N = self._patch_engine.geometry(img)
-        primed = ln_mode() == "fold"
-        ws = eng.workspace(B * N, img.device) if primed else None
-        x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
-                                         stats=ws["stats_in"] if primed else None)
-        D = x.shape[1]
-        eng.run_blocks(x, B, N, primed=primed)
         dev = img.device
-        xf = torch.empty_like(x)
-        eng.final_norm(x, out_f32=xf)
-        pm = torch.empty(B, D, device=dev, dtype=torch.float32)
-        _lib.mean_pool(xf, pm, B, N, D)
+        if transformer_is_hooked(self):                # Extractor-style hook on .transformer: tokens through the module
+            pm = fused_mean_pooled_features(self, img)
+            B, D = pm.shape
+        else:
+            B, N = self._patch_engine.geometry(img)
+            primed = ln_mode() == "fold"
+            ws = eng.workspace(B * N, img.device) if primed else None
+            x, B, N = self._patch_engine.run(img, xb=ws["xn"] if primed else None,
+                                             stats=ws["stats_in"] if primed else None)
+            D = x.shape[1]
+            eng.run_blocks(x, B, N, primed=primed)
+            xf = torch.empty_like(x)
+            eng.final_norm(x, out_f32=xf)
+            pm = torch.empty(B, D, device=dev, dtype=torch.float32)
+            _lib.mean_pool(xf, pm, B, N, D)
         pooled = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
         _lib.cast_f32_bf16(pm, pooled)
         pooled = self.to_latent(pooled)

@@ -130,7 +130,7 @@ class SimpleViT(FusedWeightsMixin, nn.Module):
         if len(self.transformer.layers) == 0:
             return "depth == 0"
         r = why_not_fused(list(self.parameters()), img, training=self.training, dropout_p=0.0)
-        if r is None and hooks_inside(self, skip=(self.to_latent,)):
+        if r is None and hooks_inside(self, skip=(self.to_latent, self.transformer)):
             r = "forward hooks registered inside the model"
         if r is None:
             ph, pw = self.patch_size

@@ -20,8 +20,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, hooks_inside, ln_mode,
-                     on_device, why_not_fused)
+from .engine import (FusedWeightsMixin, HeadEngine, PatchEmbedEngine, TransformerEngine, hooked_transformer_tokens,
+                     hooks_inside, ln_mode, on_device, transformer_is_hooked, why_not_fused)
 
 
 def pair(t):
@@ -189,7 +189,7 @@ class ViT(FusedWeightsMixin, nn.Module):
             return "depth == 0"
         p_drop = max(self._emb_dropout_p, self.transformer.dropout_p)
         r = why_not_fused(list(self.parameters()), img, training=self.training, dropout_p=p_drop)
-        if r is None and hooks_inside(self, skip=(self.to_latent,)):
+        if r is None and hooks_inside(self, skip=(self.to_latent, self.transformer)):
             r = "forward hooks registered inside the model"
         if r is None:
             ph, pw = self.patch_size
@@ -222,6 +222,16 @@ class ViT(FusedWeightsMixin, nn.Module):
         if self._patch_engine is None:
             self._patch_engine = PatchEmbedEngine(self)
         eng = self.transformer.engine()
+        if transformer_is_hooked(self):                # Extractor (reference extractor.py:50-59): hook on .transformer
+            x, B, N = self._patch_engine.run(img)
+            out = hooked_transformer_tokens(self, x, B, N)
+            if self.mlp_head is None:
+                return out
+            pooled = (out.mean(dim=1) if self.pool == 'mean' else out[:, 0]).contiguous()
+            pooled = self.to_latent(pooled)
+            if self._head_engine is None:
+                self._head_engine = HeadEngine(self.mlp_head)
+            return self._head_engine.run(pooled)
         B, N = self._patch_engine.geometry(img)
         primed = ln_mode() == "fold"
         ws = eng.workspace(B * N, img.device) if primed else None
