@@ -86,7 +86,8 @@ def test_navit_config5_geometry_against_reference_golden():
     assert torch.equal(out, out_rows)
 
 
-@pytest.mark.parametrize("mode", [0, 1])      # 0: pipelined 64-key blocks (default); 1: serial 128-key blocks
+# 0: pipelined 64-key blocks, one pass (default); 1: serial 128-key blocks; 2: pipelined, two passes (max first)
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_varlen_attention_kernel_against_oracle(mode):
     lengths = [197, 1, 130, 577, 64, 1024, 129, 65, 63, 128, 300]
     H, dh = 3, 64
@@ -109,6 +110,64 @@ def test_varlen_attention_kernel_against_oracle(mode):
         o += n
     mx, mean, frac = _stats(out, ref)
     assert frac > 0.995 and mx < 2e-2, (mx, mean, frac)
+
+
+@pytest.mark.parametrize("pattern", ["rising", "falling", "spike_late", "mixed_rows"])
+def test_varlen_attention_one_pass_moves_its_reference_max(pattern):
+    """The default one-pass kernel takes exponentials against a reference max that it only moves when a later key
+    block exceeds it by more than 2^24, rescaling O in TMEM.  Scores built to rise by ~2^40 per 64-key block (every
+    block triggers the rescale), to fall, to spike in the last block only, and to do so for some rows of a warp only;
+    same expectation (fp32 softmax on the CPU) as the ordinary test, and equal to the two-pass kernel's output."""
+    lengths = [700, 130, 64, 321]
+    H, dh = 2, 64
+    T = sum(lengths)
+    g = torch.Generator().manual_seed(3)
+    u = torch.randn(dh, generator=g)
+    u = u / u.norm()
+    q = torch.randn(T, H, dh, generator=g) * 0.05
+    k = torch.randn(T, H, dh, generator=g) * 0.05
+    v = torch.randn(T, H, dh, generator=g)
+    o = 0
+    for n in lengths:
+        pos = torch.arange(n, dtype=torch.float32)
+        blk = (pos // 64)
+        if pattern == "rising":
+            amp = blk + 1.0
+        elif pattern == "falling":
+            amp = (n // 64 + 1) - blk
+        elif pattern == "spike_late":
+            amp = torch.where(blk == (n - 1) // 64, torch.tensor(6.0), torch.tensor(0.1))
+        else:
+            amp = blk + 1.0
+        # score(i, j) = 240 * amp_j * (+-1)  (scale 1/8 -> 30 * amp_j in softmax units, x 1.44 in log2 units)
+        sign = torch.ones(n)
+        if pattern == "mixed_rows":
+            sign = torch.where(torch.arange(n) % 3 == 0, torch.tensor(-1.0), torch.tensor(1.0))
+        q[o:o + n] += (sign[:, None, None] * 15.5) * u
+        k[o:o + n] += (amp[:, None, None] * 15.5) * u
+        o += n
+    qkv = torch.stack([q, k, v], dim=1).reshape(T, 3 * H * dh).bfloat16().to(DEV)
+    cu, tp, tiles = _lib.varlen_index(lengths, DEV)
+    outs = {}
+    for mode in (0, 2):
+        out = torch.zeros(T, H * dh, device=DEV, dtype=torch.bfloat16)
+        _lib.lib().b200vit_debug_set(11, mode)
+        try:
+            _lib.attention_varlen(qkv, out, cu, tp, tiles, H, dh, dh ** -0.5)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().b200vit_debug_set(11, 0)
+        outs[mode] = out.float().cpu()
+    ref = torch.empty(T, H * dh)
+    o = 0
+    for n in lengths:
+        qq, kk, vv = qkv[o:o + n].float().cpu().view(n, 3, H, dh).permute(1, 2, 0, 3)
+        ref[o:o + n] = (O.softmax_last((qq @ kk.transpose(-1, -2)) * dh ** -0.5) @ vv).permute(1, 0, 2).reshape(n, H * dh)
+        o += n
+    assert torch.isfinite(outs[0]).all()
+    mx, mean, frac = _stats(outs[0], ref)
+    assert frac > 0.99 and mx < 3e-2, (pattern, mx, mean, frac)
+    assert (outs[0] - outs[2]).abs().max() < 2e-2
 
 
 @pytest.mark.parametrize("H", [3, 4, 16])

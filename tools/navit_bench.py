@@ -13,6 +13,8 @@ from vit_pytorch_b200 import NaViT, _lib  # noqa: E402
 
 def main():
     dev = "cuda"
+    mode = int(os.environ.get("VARLEN_MODE", "0"))      # varlen attention kernel (b200vit_debug_set key 11)
+    _lib.lib().b200vit_debug_set(11, mode)
     kwargs = dict(image_size=512, patch_size=16, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=4096)
     torch.manual_seed(0)
     m = NaViT(**kwargs).eval().to(dev, torch.bfloat16)
@@ -41,7 +43,7 @@ def main():
         by[name] = by.get(name, 0.0) + t
     gemm_flops = sum(meta.get("flops", 0.0) for name, meta, t in rec if name == "gemm")
     attn_flops = 6 * sum(4.0 * 16 * ((h // 16) * (w // 16)) ** 2 * 64 for h, w in sizes)
-    print(json.dumps({"workload": "NaViT config 5: 256 images, %d tokens, padding-free" % tokens, "ms": ms,
+    print(json.dumps({"varlen_mode": mode, "workload": "NaViT config 5: 256 images, %d tokens, padding-free" % tokens, "ms": ms,
                       "images_per_s": 256 / ms * 1e3, "tokens_per_s": tokens / ms * 1e3,
                       "tflops_algorithmic": (gemm_flops + attn_flops) / ms / 1e9,
                       "finite": bool(torch.isfinite(out.float()).all()),

@@ -316,7 +316,7 @@ constexpr int THREADS = 6 * 32;
 __device__ __forceinline__ uint32_t buf_col(int bf) { return bf == 2 ? 192u : static_cast<uint32_t>(bf) * KB; }
 }  // namespace av2
 
-template <bool TRACE>
+template <bool TRACE, bool ONLINE>
 __global__ void __launch_bounds__(av2::THREADS, 2)
 attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const AttnVarlenParams p) {
@@ -409,7 +409,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         stamp(units_done, 13);
         mbar_arrive_expect_tx(q_full, Q_BYTES);
         tma_load_2d(sQ, &tmQ, q_full, h * DH, row0 + qt * 128);
-        const int steps = (nb > 1 ? nb : 0) + nb;
+        const int steps = (!ONLINE && nb > 1 ? nb : 0) + nb;
         for (int s = 0; s < steps; ++s, ++kv_count) {
           const bool phase2 = s >= steps - nb;
           const int kb = phase2 ? s - (steps - nb) : s;
@@ -439,7 +439,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         int seq, h, qt, row0, n;
         locate(u, units_done, seq, h, qt, row0, n);
         const int nb = (n + KB - 1) / KB;
-        const int steps = (nb > 1 ? nb : 0) + nb;
+        const int steps = (!ONLINE && nb > 1 ? nb : 0) + nb;
         stamp(units_done, 8);
         mbar_wait(q_full, units_done & 1);
         stamp(units_done, 9);
@@ -515,6 +515,10 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       par_sfull ^= 1u << bf;
       bf = bf == NBUF - 1 ? 0 : bf + 1;
     };
+    // ONLINE only: pv_done[b] completes once per step on buffer b (barrier phases run on across units)
+    uint32_t par_pv = 0;       // bit b: parity of the next completion of pv_done[b]
+    int prev_bf = 0;
+    uint32_t prev_par = 0;     // (buffer, parity) of the completion of the previous step's P V
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++units_done) {
       const bool tr0 = TRACE && warp == 0 && lane == 0;
       if (tr0) stamp(units_done, 0);
@@ -527,6 +531,101 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       const int qrow = qt * 128 + quad * 32 + lane;
       float mx = -INFINITY;
+      float sum = 0.f;
+      if constexpr (ONLINE) {
+        // ---- one pass: exponentials are taken against a REFERENCE max `mx` that is only moved when a block's max
+        // exceeds it by more than 2^TAU (P is bf16 and sum / O are fp32: a stale reference costs range, not
+        // precision); moving it rescales this warp's rows of O in TMEM, after the P V issued so far have completed.
+        constexpr float TAU = 24.f;      // log2 units: P <= 2^24, sum and O stay far inside fp32 range
+        for (int kb = 0; kb < nb; ++kb) {
+          const uint32_t tb = t_lane + buf_col(bf);
+          mbar_wait(&s_full[bf], (par_sfull >> bf) & 1);
+          if (tr0 && kb == 0) stamp(units_done, 4);
+          tc_fence_after();
+          const int lim = n - kb * KB;   // valid keys of this block, >= 1 (warp-uniform)
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tb, r0);
+          if (lim > 32) tmem_ld_32x32b_x32(tb + 32, r1);
+          tmem_ld_wait();
+          float bm = -INFINITY;
+          if (lim >= KB) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bm = fmaxf(bm, fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < lim) bm = fmaxf(bm, __uint_as_float(r0[j]));
+              if (j + 32 < lim) bm = fmaxf(bm, __uint_as_float(r1[j]));
+            }
+          }
+          if (kb == 0) {
+            mx = bm;
+          } else {
+            const bool grow = (bm - mx) * c > TAU;
+            if (__any_sync(0xffffffffu, grow)) {
+              const float f = grow ? fast_ex2((mx - bm) * c) : 1.f;
+              if (grow) mx = bm;
+              sum *= f;
+              mbar_wait(&pv_done[prev_bf], prev_par);      // O holds every block before this one
+              tc_fence_after();
+#pragma unroll 1
+              for (int c0 = 0; c0 < DH; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld_32x32b_x16(t_lane + O_COL + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                tmem_st_32x32b_x16(t_lane + O_COL + c0, o);
+              }
+            }
+          }
+          const float mc = mx * c;
+          uint32_t pk[16];
+          if (lim >= KB) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = fast_ex2(fmaf(__uint_as_float(r0[j]), c, -mc));
+              const float e1 = fast_ex2(fmaf(__uint_as_float(r0[j + 1]), c, -mc));
+              sum += e0 + e1;
+              pk[j >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x16(tb, pk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = fast_ex2(fmaf(__uint_as_float(r1[j]), c, -mc));
+              const float e1 = fast_ex2(fmaf(__uint_as_float(r1[j + 1]), c, -mc));
+              sum += e0 + e1;
+              pk[j >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x16(tb + 16, pk);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = (j < lim) ? fast_ex2(fmaf(__uint_as_float(r0[j]), c, -mc)) : 0.f;
+              const float e1 = (j + 1 < lim) ? fast_ex2(fmaf(__uint_as_float(r0[j + 1]), c, -mc)) : 0.f;
+              sum += e0 + e1;
+              pk[j >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x16(tb, pk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = (j + 32 < lim) ? fast_ex2(fmaf(__uint_as_float(r1[j]), c, -mc)) : 0.f;
+              const float e1 = (j + 33 < lim) ? fast_ex2(fmaf(__uint_as_float(r1[j + 1]), c, -mc)) : 0.f;
+              sum += e0 + e1;
+              pk[j >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st_32x32b_x16(tb + 16, pk);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[bf]);
+          prev_bf = bf;
+          prev_par = (par_pv >> bf) & 1;
+          par_pv ^= 1u << bf;
+          next_buf();
+        }
+      } else {
       auto block_max = [&](int kb, uint32_t tb) {
 #pragma unroll 1
         for (int c0 = 0; c0 < KB; c0 += 32) {
@@ -552,7 +651,6 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           next_buf();
         }
       }
-      float sum = 0.f;
       if (tr0) stamp(units_done, 3);
       for (int kb = 0; kb < nb; ++kb) {
         const uint32_t tb = t_lane + buf_col(bf);
@@ -584,6 +682,7 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[bf]);
         next_buf();
+      }
       }
       // epilogue: O / sum -> bf16 -> global
       if (tr0) stamp(units_done, 5);
@@ -623,7 +722,9 @@ attention_varlen2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
 static long long* g_varlen_trace = nullptr;
 void attention_varlen_set_trace(long long* buf) { g_varlen_trace = buf; }
-static int g_varlen_mode = 0;  // 0: pipelined 64-key blocks (default), 1: the serial 128-key-block kernel
+// 0: pipelined 64-key blocks, one pass with a lazily moved reference max (default); 1: the serial 128-key-block kernel;
+// 2: pipelined 64-key blocks, two passes (max first)
+static int g_varlen_mode = 0;
 void attention_varlen_set_mode(int v) { g_varlen_mode = v; }
 
 }  // namespace b200
@@ -653,18 +754,23 @@ extern "C" int b200vit_attention_varlen(const void* qkv, void* out, const int32_
   const int slots = 2 * num_sms();
   const int grid = p.units < slots ? p.units : slots;
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (g_varlen_mode == 0) {
+  if (g_varlen_mode != 1) {
+    const bool online = g_varlen_mode == 0;
     CUtensorMap tmQ, tmKV;
     const uint32_t qbox[2] = {64, 128}, kvbox[2] = {64, (uint32_t)av2::KB};
     int rc = encode_tmap_bf16(&tmQ, qkv, 2, dims, strides, qbox);
     if (rc) return rc;
     rc = encode_tmap_bf16(&tmKV, qkv, 2, dims, strides, kvbox);
     if (rc) return rc;
-    B200_ENSURE_SMEM(attention_varlen2_kernel<false>, av2::DYN_BYTES);
-    B200_ENSURE_SMEM(attention_varlen2_kernel<true>, av2::DYN_BYTES);
     p.trace = g_varlen_trace;
-    if (p.trace) attention_varlen2_kernel<true><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
-    else attention_varlen2_kernel<false><<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
+    auto run = [&](auto kern) -> int {
+      B200_ENSURE_SMEM(kern, av2::DYN_BYTES);
+      kern<<<grid, av2::THREADS, av2::DYN_BYTES, st>>>(tmQ, tmKV, p);
+      return 0;
+    };
+    if (p.trace) rc = online ? run(attention_varlen2_kernel<true, true>) : run(attention_varlen2_kernel<true, false>);
+    else rc = online ? run(attention_varlen2_kernel<false, true>) : run(attention_varlen2_kernel<false, false>);
+    if (rc) return rc;
   } else {
     CUtensorMap tm;
     const uint32_t box[2] = {64, 128};
