@@ -241,7 +241,7 @@ def test_extractor_hook_keeps_the_fused_path(kind):
         _lib.reset_launch_count()
         pred, emb = ext(img)
         assert _lib.launch_count() >= 3 + 5 * 2
-        n = 64 + (0 if kind == "simple" else 1)
+        n = 64 + (1 if kind == "vit_cls" else 0)         # pool="mean" has no cls token (vit.py:105-106)
         assert emb.shape == (3, n, 128) and emb.dtype == torch.bfloat16
         assert (pred.float() - plain.float()).abs().max() < 2e-2          # tokens passed through bf16 once
         ext.eject()

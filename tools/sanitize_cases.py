@@ -40,11 +40,14 @@ if "attention" in which:
         o = torch.zeros(B * N, H * 64, device=dev, dtype=torch.bfloat16)
         _lib.attention(qkv, o, B, N, H, 64, 0.125)
     L.b200vit_debug_set(1, 0)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         L.b200vit_debug_set(11, mode)
         lengths = [197, 1, 130, 300, 64]
         T = sum(lengths)
         qkv = torch.randn(T, 3 * 2 * 64, device=dev).bfloat16()
+        # keys growing along the sequence: the one-pass kernel (mode 0) moves its reference max and rescales O in TMEM
+        qkv[:, 128:256] = (qkv[:, 128:256].float() * (1 + torch.arange(T, device=dev)[:, None] / 8.0)).bfloat16()
+        qkv[:, :128] = (qkv[:, :128].float() * 4).bfloat16()
         o = torch.zeros(T, 2 * 64, device=dev, dtype=torch.bfloat16)
         cu, tp, tiles = _lib.varlen_index(lengths, dev)
         _lib.attention_varlen(qkv, o, cu, tp, tiles, 2, 64, 0.125)

@@ -584,25 +584,28 @@ rmsnorm_heads_kernel(__nv_bfloat16* __restrict__ buf, long long ld, const float*
 
 // NaViT attention pooling (reference na_vit.py:371-387): one learned query per image attends to that image's tokens.
 //   kv[T, 2*H*64] bf16 (k already RMS-normalised, then v), qn[H*64] fp32 (normalised query), sequences by cu_seqlens;
-//   out[S, H*64] bf16 = softmax_j(qn_h . k_jh) v_jh   (scale 1).  One warp per (image, head), online softmax.
-__global__ void __launch_bounds__(128)
+//   out[S, H*64] bf16 = softmax_j(qn_h . k_jh) v_jh   (scale 1).  One CTA of 8 warps per (image, head): warp w walks the
+//   token groups w, w + 8, ... (4 tokens each) with an online softmax, the 8 partial (max, sum, acc) are merged in
+//   shared memory -- a 1024-token image no longer takes 64x the time of a 16-token one on a single warp.
+__global__ void __launch_bounds__(256)
 attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__ qn, const int* __restrict__ cu,
                  __nv_bfloat16* __restrict__ out, int S, int H) {
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  constexpr int NW = 8;
+  __shared__ float part[NW][4 + 64];   // m, l, -, -, acc[64]
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= S * H) return;
-  const int s = w / H, h = w % H;
+  const int s = blockIdx.x / H, h = blockIdx.x % H;
   const int I = H * 64;
   const float2 q = *reinterpret_cast<const float2*>(qn + h * 64 + 2 * lane);
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-  const int j1 = cu[s + 1];
-  int j = cu[s];
+  const int j0 = cu[s], j1 = cu[s + 1];
   // four tokens per step: eight independent loads and four interleaved butterflies, one rescale of the running sums
-  for (; j + 4 <= j1; j += 4) {
+  for (int j = j0 + 4 * warp; j < j1; j += 4 * NW) {
+    const int cnt = j1 - j < 4 ? j1 - j : 4;
     float2 k[4], v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat16* r = kv + (long long)(j + i) * 2 * I + h * 64;
+      const __nv_bfloat16* r = kv + (long long)(j + (i < cnt ? i : 0)) * 2 * I + h * 64;
       k[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r) + lane));
       v[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r + I) + lane));
     }
@@ -614,6 +617,9 @@ attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
     }
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+      if (i >= cnt) sc[i] = -INFINITY;         // tail group: the duplicated token 0 gets weight 0
     const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
     const float corr = __expf(m - mn);
     l *= corr; a0 *= corr; a1 *= corr;
@@ -626,20 +632,28 @@ attn_pool_kernel(const __nv_bfloat16* __restrict__ kv, const float* __restrict__
     }
     m = mn;
   }
-  for (; j < j1; ++j) {
-    const __nv_bfloat16* r = kv + (long long)j * 2 * I + h * 64;
-    const float2 k = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r) + lane));
-    const float2 v = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(r + I) + lane));
-    const float sc = warp_sum(q.x * k.x + q.y * k.y);
-    const float mn = fmaxf(m, sc);
-    const float corr = __expf(m - mn), pj = __expf(sc - mn);
-    l = l * corr + pj;
-    a0 = a0 * corr + pj * v.x;
-    a1 = a1 * corr + pj * v.y;
-    m = mn;
+  if (lane == 0) {
+    part[warp][0] = m;
+    part[warp][1] = l;
   }
-  const float inv = 1.0f / l;
-  *(reinterpret_cast<__nv_bfloat162*>(out + (long long)s * I + h * 64) + lane) = __floats2bfloat162_rn(a0 * inv, a1 * inv);
+  part[warp][4 + 2 * lane] = a0;
+  part[warp][5 + 2 * lane] = a1;
+  __syncthreads();
+  if (warp == 0) {
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, part[w][0]);
+    float L = 0.f, A0 = 0.f, A1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float f = part[w][0] == -INFINITY ? 0.f : __expf(part[w][0] - mm);   // warps without a token
+      L = fmaf(part[w][1], f, L);
+      A0 = fmaf(part[w][4 + 2 * lane], f, A0);
+      A1 = fmaf(part[w][5 + 2 * lane], f, A1);
+    }
+    const float inv = 1.0f / L;
+    *(reinterpret_cast<__nv_bfloat162*>(out + (long long)s * I + h * 64) + lane) = __floats2bfloat162_rn(A0 * inv, A1 * inv);
+  }
 }
 
 // NaViT token assembly for packed variable-size images (reference na_vit.py:228,350-359): LayerNorm(dim, no bias) of
@@ -758,7 +772,7 @@ extern "C" int b200vit_attn_pool(const void* kv, const float* qn, const int32_t*
                                  int H, int dh, void* stream) {
   B200_CHECK_ARG(kv && qn && cu_seqlens_dev && out && S > 0 && H > 0, "attn_pool: bad argument");
   B200_CHECK_ARG(dh == 64, "attn_pool: dim_head=%d not supported by this build (only 64)", dh);
-  attn_pool_kernel<<<(S * H + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  attn_pool_kernel<<<S * H, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(kv), qn, cu_seqlens_dev, reinterpret_cast<__nv_bfloat16*>(out), S, H);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
