@@ -121,7 +121,7 @@ int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, in
  *   out[B*N, H*dh]   bf16 (merged heads, vit.py:63) = softmax(q k^T * scale) v          (vit.py:57-62)
  * One pass over the keys (N <= 512): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
  * dh = 64, or 80 (canonical ViT-H/14): an 80-wide head is staged as a 64-wide + a 16-wide shared-memory slab.
- * N <= 224: software-pipelined kernel (attention_pipe.cu: two score regions + one O slot per SM, K/V once per head).
+ * (A software-pipelined variant for N <= 224, attention_pipe.cu, is built but only reachable through the test hook.)
  */
 int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
 
@@ -204,12 +204,49 @@ int b200vit_mean_pool(const float* x, float* out, int B, int N, int D, int n_poo
 int b200vit_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
 
 /*
+ * All encoder layers in one call (vit.py:78-81 / simple_vit.py:74-77), LayerNorm-folded schedule: per layer
+ *   b200vit_gemm_bf16 (LN fold; b200vit_gemm_headnorm_bf16 if qk_gamma) -> b200vit_attention (N <= 512, else
+ *   b200vit_attention_varlen) -> b200vit_gemm_bf16 (+ residual, statistics) -> b200vit_gemm_bf16 (LN fold, GELU)
+ *   -> b200vit_gemm_bf16 (+ residual, statistics).
+ * The host-side loop below the language boundary: one call instead of 5 x depth (small batches are host bound).
+ * Weights are the LN-folded forms the Python engine prepares (engine.py TransformerEngine.prepared):
+ *   *_wg = gamma (.) W rounded to bf16, *_s[n] = sum_k wg[n, k] (fp32, from the rounded weights), *_t = W beta (+ bias).
+ * x[B*N, D] fp32 is the residual stream, updated in place.  primed != 0: ws->xb (bf16 copy of x) and ws->stats_in
+ * ([M][2] row (sum, sum of squares) of that copy) were written by b200vit_embed_tokens; else they are computed here.
+ * ws->stats_a / stats_b: [M][b200vit_stats_parts(D)][2] fp32 scratch; ws->qkv [M, 3*heads*dh], ws->o [M, heads*dh],
+ * ws->h [M, hidden] bf16 scratch.  cu_seqlens / tile_prefix / total_tiles: only for N > 512 (B sequences of N tokens).
+ */
+typedef struct b200vit_layer {
+  const void* qkv_wg;      /* [3*heads*dh, D] bf16 */
+  const float* qkv_t;      /* [3*heads*dh] */
+  const float* qkv_s;      /* [3*heads*dh] */
+  const float* qk_gamma;   /* NULL, or [2][heads][dh]: per-head q / k RMSNorm (simple_vit_with_qk_norm.py:60-67) */
+  const void* out_w;       /* [D, heads*dh] bf16 */
+  const float* out_b;      /* [D] or NULL */
+  const void* fc1_wg;      /* [hidden, D] bf16 */
+  const float* fc1_t;      /* [hidden] */
+  const float* fc1_s;      /* [hidden] */
+  const void* fc2_w;       /* [D, hidden] bf16 */
+  const float* fc2_b;      /* [D] or NULL */
+  float ln1_eps, ln2_eps;
+} b200vit_layer;
+typedef struct b200vit_encoder_ws {
+  void *xb, *qkv, *o, *h;
+  float *stats_in, *stats_a, *stats_b;
+} b200vit_encoder_ws;
+int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, float* x, const b200vit_encoder_ws* ws, int B, int N,
+                           int D, int heads, int dh, int hidden, float scale, int primed,
+                           const int32_t* cu_seqlens_dev, const int32_t* tile_prefix_dev, int total_tiles,
+                           void* stream);
+
+/*
  * TEST HOOKS -- process-global switches for A/B tests and bring-up; NOT part of the re-entrant API above (a value set
  * here changes every later call of every thread).  Production code never calls them.
  *   key 1: b200vit_attention kernel choice: 0 = auto, 1 = round-1 kernels only, 2 = pipelined kernel wherever N <= 224
  *   key 2 / 3: V (MN-major) descriptor LBO / SBO bytes (bring-up probe)
  *   key 4: GEMM kernel choice: 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair kernel wherever its epilogue applies
- *   key 11: varlen attention kernel: 0 = pipelined 64-key blocks (default), 1 = serial 128-key blocks
+ *   key 11: varlen attention kernel: 0 = pipelined 64-key blocks, one pass (default), 1 = serial 128-key blocks,
+ *           2 = pipelined 64-key blocks, two passes (exact max first)
  *   key 12: fp32-epilogue warps of the CTA-pair GEMM: 0 = auto (4 when K >= 2048, else 8), 4 / 8 = forced
  *   key 14 / 15: dim_head 80: LBO / SBO bytes of the 16-wide V slab descriptor (bring-up probe)
  *   key 13: pipelined attention: 0 = all softmax exponentials on MUFU (default), 1 = half of them on the FMA pipe

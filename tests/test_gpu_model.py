@@ -267,3 +267,38 @@ def test_hook_inside_the_transformer_still_forces_the_pytorch_graph():
         rec.eject()
         assert m.fused_reason(img) is None
         assert (m(img).float() - pred.float()).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("case", ["vit_golden", "qk_norm", "long_sequence", "dh80"])
+def test_one_call_encoder_equals_the_per_kernel_host_loop(case, monkeypatch):
+    """b200vit_encoder_blocks (all layers in one C-ABI call, the default) launches exactly the kernels the Python loop
+    launches, with the same arguments: bit-identical logits and the same launch count."""
+    torch.manual_seed(0)
+    if case == "vit_golden":
+        g = load_golden("vit_tiny_cls")
+        m = fused_model(g)
+        x = g["input"].to(DEV)
+    elif case == "qk_norm":
+        from vit_pytorch_b200.simple_vit_with_qk_norm import SimpleViT as QK
+        m = QK(image_size=64, patch_size=8, num_classes=7, dim=128, depth=2, heads=2, mlp_dim=256).eval()
+        m = m.to(DEV, torch.bfloat16)
+        x = torch.randn(3, 3, 64, 64, device=DEV).bfloat16()
+    elif case == "long_sequence":
+        m = ViT(image_size=224, patch_size=8, num_classes=5, dim=128, depth=2, heads=2, mlp_dim=256).eval()
+        m = m.to(DEV, torch.bfloat16)                     # N = 785 > 512: key-block attention inside the C loop
+        x = torch.randn(2, 3, 224, 224, device=DEV).bfloat16()
+    else:
+        m = ViT(image_size=56, patch_size=14, num_classes=5, dim=160, depth=2, heads=2, dim_head=80, mlp_dim=320).eval()
+        m = m.to(DEV, torch.bfloat16)
+        x = torch.randn(4, 3, 56, 56, device=DEV).bfloat16()
+    outs, counts = {}, {}
+    for loop in ("c", "python"):
+        monkeypatch.setenv("B200VIT_HOST_LOOP", loop)
+        _lib.reset_launch_count()
+        with torch.inference_mode():
+            assert m.fused_reason(x) is None, m.fused_reason(x)
+            outs[loop] = m(x).clone()
+        torch.cuda.synchronize()
+        counts[loop] = _lib.launch_count()
+    assert torch.equal(outs["c"], outs["python"])
+    assert counts["c"] == counts["python"] > 0

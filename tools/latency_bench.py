@@ -44,12 +44,15 @@ def main():
         img = torch.randn(B, 3, 224, 224, device=dev).bfloat16()
         n = 200 if B <= 64 else 20
         with torch.inference_mode():
+            os.environ["B200VIT_HOST_LOOP"] = "python"          # one ctypes call per kernel (the round-2 mid state)
+            fused_py = wall_ms(lambda: model(img), n)
+            os.environ["B200VIT_HOST_LOOP"] = "c"               # all layers in one b200vit_encoder_blocks call (default)
             fused = wall_ms(lambda: model(img), n)
             g = GraphedForward(model, img)
             same = bool(torch.equal(g(img), model(img)))
             graphed = wall_ms(lambda: g(img), n)
             eager = wall_ms(lambda: ref(img), n) if ref is not None else None
-        out[B] = {"fused_ms": round(fused, 3), "fused_graph_ms": round(graphed, 3),
+        out[B] = {"fused_ms": round(fused, 3), "fused_python_loop_ms": round(fused_py, 3), "fused_graph_ms": round(graphed, 3),
                   "reference_eager_ms": None if eager is None else round(eager, 3), "graph_bit_identical": same}
         print(B, out[B], file=sys.stderr, flush=True)
     print(json.dumps({"model": "ViT-B/16 224^2 bf16 forward, wall clock per call", "batches": out}))

@@ -31,7 +31,22 @@ SYMBOLS = [
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
     "b200vit_patchify_varlen_ln", "b200vit_rmsnorm_heads", "b200vit_embed_varlen",
     "b200vit_gemm_headnorm_bf16", "b200vit_layernorm_heads", "b200vit_patch_stats", "b200vit_patch_embed_tma",
+    "b200vit_encoder_blocks",
 ]
+
+
+class Layer(C.Structure):
+    """struct b200vit_layer (include/b200vit.h): LN-folded weights of one encoder layer, raw device pointers."""
+    _fields_ = [("qkv_wg", C.c_void_p), ("qkv_t", C.c_void_p), ("qkv_s", C.c_void_p), ("qk_gamma", C.c_void_p),
+                ("out_w", C.c_void_p), ("out_b", C.c_void_p), ("fc1_wg", C.c_void_p), ("fc1_t", C.c_void_p),
+                ("fc1_s", C.c_void_p), ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+                ("ln1_eps", C.c_float), ("ln2_eps", C.c_float)]
+
+
+class EncoderWs(C.Structure):
+    """struct b200vit_encoder_ws: scratch buffers of b200vit_encoder_blocks."""
+    _fields_ = [("xb", C.c_void_p), ("qkv", C.c_void_p), ("o", C.c_void_p), ("h", C.c_void_p),
+                ("stats_in", C.c_void_p), ("stats_a", C.c_void_p), ("stats_b", C.c_void_p)]
 
 _lib: Optional[C.CDLL] = None
 
@@ -100,6 +115,9 @@ def lib() -> C.CDLL:
     L.b200vit_mean_pool.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.b200vit_cast_f32_bf16.restype = i32
     L.b200vit_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
+    L.b200vit_encoder_blocks.restype = i32
+    L.b200vit_encoder_blocks.argtypes = [C.POINTER(Layer), i32, vp, C.POINTER(EncoderWs), i32, i32, i32, i32, i32, i32,
+                                         f32, i32, vp, vp, i32, vp]
     _lib = L
     return L
 
@@ -156,6 +174,23 @@ class _Timed:
             self.e1.record()
             _prof.append((self.name, self.meta, self.e0, self.e1))
         return False
+
+
+def profiling() -> bool:
+    """True between profile_start() and profile_stop(): callers that batch several kernels into one library call
+    (encoder_blocks) go call by call instead, so that every kernel gets its own events."""
+    return _prof is not None
+
+
+def encoder_blocks(layers, depth: int, x: torch.Tensor, ws: "EncoderWs", B: int, N: int, D: int, heads: int, dh: int,
+                   hidden: int, scale: float, primed: bool, varlen=None) -> None:
+    """All encoder layers in one library call (b200vit_encoder_blocks).  `layers`: ctypes array of Layer built from the
+    prepared weights; `ws`: EncoderWs over the engine's workspace; `varlen`: (cu, tile_prefix, total_tiles) if N > 512."""
+    _chk(x, torch.float32, "x")
+    cu, tp, tiles = varlen if varlen is not None else (None, None, 0)
+    rc = lib().b200vit_encoder_blocks(layers, depth, _ptr(x), C.byref(ws), B, N, D, heads, dh, hidden, float(scale),
+                                      1 if primed else 0, _ptr(cu), _ptr(tp), int(tiles), _stream())
+    _check(rc, "b200vit_encoder_blocks")
 
 
 def launch_count() -> int:

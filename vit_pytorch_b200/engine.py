@@ -26,6 +26,7 @@ from . import _lib
 _FORCE_EAGER_ENV = "B200VIT_DISABLE_FUSED"
 _LN_MODE_ENV = "B200VIT_LN_MODE"      # "fold" (default) | "exact"
 _PATCH_MODE_ENV = "B200VIT_PATCH_MODE"  # "tma" (default: im2col-free 16x16 patch embedding) | "gather"
+_HOST_LOOP_ENV = "B200VIT_HOST_LOOP"    # "c" (default: all layers in one b200vit_encoder_blocks call) | "python"
 
 
 def ln_mode() -> str:
@@ -177,6 +178,7 @@ class TransformerEngine:
         self.prep = _Prepared()
         self.ws_key: Optional[tuple] = None
         self.ws: Dict[str, torch.Tensor] = {}
+        self.c_ws = None                       # _lib.EncoderWs over self.ws
 
     # -------------------------------------------------------------------------------------------- structure
     def _layers(self):
@@ -242,8 +244,29 @@ class TransformerEngine:
             t[f"{i}.fc2.w"], t[f"{i}.fc2.b"] = _bf16_rows(fc2.weight), _f32(fc2.bias)
         if self.has_final_norm():
             t["norm.w"], t["norm.b"] = _f32(self.mod.norm.weight), _f32(self.mod.norm.bias)
+        t["c_layers"] = self._c_layers(t)            # type: ignore[assignment]
         self.prep.key, self.prep.t = key, t
         return t
+
+    def _c_layers(self, t: Dict[str, torch.Tensor]):
+        """(ctypes array of b200vit_layer, heads, dh, hidden, scale) for the one-call encoder (b200vit_encoder_blocks),
+        or None when the layers are not uniform.  The pointers stay valid as long as `t` (which holds the tensors)."""
+        layers = list(self._layers())
+        a0, f0 = layers[0]
+        sig = (a0.heads, a0.dim_head, f0.hidden_dim, _softmax_scale(a0))
+        if any((a.heads, a.dim_head, f.hidden_dim, _softmax_scale(a)) != sig for a, f in layers):
+            return None
+        arr = (_lib.Layer * len(layers))()
+        p = lambda v: None if v is None else v.data_ptr()      # noqa: E731
+        for i, (attn, ff) in enumerate(layers):
+            L = arr[i]
+            L.qkv_wg, L.qkv_t, L.qkv_s = p(t[f"{i}.qkv.wg"]), p(t[f"{i}.qkv.t"]), p(t[f"{i}.qkv.s"])
+            L.qk_gamma = p(t.get(f"{i}.gqk"))
+            L.out_w, L.out_b = p(t[f"{i}.out.w"]), p(t[f"{i}.out.b"])
+            L.fc1_wg, L.fc1_t, L.fc1_s = p(t[f"{i}.fc1.wg"]), p(t[f"{i}.fc1.t"]), p(t[f"{i}.fc1.s"])
+            L.fc2_w, L.fc2_b = p(t[f"{i}.fc2.w"]), p(t[f"{i}.fc2.b"])
+            L.ln1_eps, L.ln2_eps = float(attn.norm.eps), float(ff.parts()[0].eps)
+        return arr, sig
 
     # -------------------------------------------------------------------------------------------- workspaces
     def workspace(self, M: int, device: torch.device) -> Dict[str, torch.Tensor]:
@@ -263,6 +286,9 @@ class TransformerEngine:
                 "stats_a": torch.empty(M, _lib.stats_parts(D), 2, device=device, dtype=torch.float32),
                 "stats_b": torch.empty(M, _lib.stats_parts(D), 2, device=device, dtype=torch.float32),
             }
+            w = self.ws
+            self.c_ws = _lib.EncoderWs(w["xn"].data_ptr(), w["qkv"].data_ptr(), w["o"].data_ptr(), w["h"].data_ptr(),
+                                       w["stats_in"].data_ptr(), w["stats_a"].data_ptr(), w["stats_b"].data_ptr())
             self.ws_key = key
         return self.ws
 
@@ -289,6 +315,19 @@ class TransformerEngine:
         ws = self.workspace(M, x.device)
         if ln_mode() == "fold":
             xb, sa, sb = ws["xn"], ws["stats_a"], ws["stats_b"]
+            if t["c_layers"] is not None and not _lib.profiling() and os.environ.get(_HOST_LOOP_ENV, "c") == "c":
+                # the whole layer loop below the language boundary: one ctypes call instead of 5 x depth
+                arr, (heads, dh, hidden, scale) = t["c_layers"]
+                varlen = None
+                if N > 512:
+                    key = (B, N, x.device)
+                    if getattr(self, "_vl_key", None) != key:
+                        self._vl = _lib.varlen_index([N] * B, x.device)
+                        self._vl_key = key
+                    varlen = self._vl
+                _lib.encoder_blocks(arr, len(arr), x, self.c_ws, B, N, x.shape[1], heads, dh, hidden, scale, primed,
+                                    varlen)
+                return
             if not primed:
                 _lib.rowstats_cast(x, xb, ws["stats_in"])
             for i, (attn, ff) in enumerate(self._layers()):
