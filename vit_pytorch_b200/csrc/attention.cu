@@ -31,6 +31,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   unsigned v_lbo, v_sbo;  // V (MN-major) descriptor strides, bytes
   unsigned v16_lbo, v16_sbo;  // dim_head 80: descriptor strides of the 16-wide V slab (32-byte swizzle)
+  int ktail;      // keys [N - ktail, N) are NOT in the S tile: their scores and P V terms run on the CUDA cores (<= 4)
 };
 
 __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { return kv_boxes * kv_box_rows * 128; }
@@ -44,7 +45,9 @@ __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { ret
 // DH = 64 or 80 (canonical ViT-H/14, reference vit.py:86 `dim_head`).  128-byte swizzled TMA boxes are 64 bf16 wide, so
 // an 80-wide head is staged as a 64-wide slab plus a 16-wide slab (32-byte rows, 32-byte swizzle): Q K^T gets a
 // fifth k-step from the 16-wide slabs, P V a second MMA per key step with N = 16 into O columns [64, 80).
-template <int NWG, int STAGES, int TMEM_COLS, int DH>
+// KTAIL: the last p.ktail (1..4) keys are not in the S tile -- N = 257 keeps a 256-column tile (two CTAs per SM, 256
+// TMEM columns each) and the softmax threads add the 257th key's score and P V term themselves from shared memory.
+template <int NWG, int STAGES, int TMEM_COLS, int DH, bool KTAIL = false>
 __global__ void __launch_bounds__((4 * NWG + 2) * 32, TMEM_COLS == 256 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmQ16, const __grid_constant__ CUtensorMap tmKV16,
@@ -70,6 +73,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* o_full = p_ready + NWG;
   uint64_t* o_free = o_full + NWG;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + NWG);
+  uint8_t* vtail = reinterpret_cast<uint8_t*>(bars) + 256;   // KTAIL: [4][DH] bf16, V rows of the tail keys (host adds 1 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -236,11 +240,76 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       mbar_wait(&s_full[t], up);
       tc_fence_after();
+      const uint8_t* stage = smem + (it % STAGES) * stage_bytes;
+      if constexpr (KTAIL) {
+        // the tail keys' V rows leave the stage before P V is released (after it the producer refills the stage):
+        // un-swizzled copy into a scratch area every softmax thread reads in the epilogue.  All four warps pass here
+        // (also the ones without valid rows); the previous unit's readers are done (they have arrived on o_free,
+        // which S of this unit waited for).
+        mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);     // TMA bytes visible to THIS thread
+        if (quad == 0) {
+          const int nk0 = p.N - p.ktail;
+          for (int idx = lane; idx < p.ktail * (DH / 8); idx += 32) {
+            const int tt = idx / (DH / 8), ch = idx % (DH / 8);
+            const int kr = nk0 + tt;
+            const uint8_t* src = ch < 8 ? stage + kv_bytes + kr * 128 + ((ch ^ (kr & 7)) << 4)
+                                        : stage + kv_bytes + kv64_bytes + kr * 32 + (((ch - 8) ^ ((kr >> 2) & 1)) << 4);
+            *reinterpret_cast<uint4*>(vtail + tt * (DH * 2) + ch * 16) = *reinterpret_cast<const uint4*>(src);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       float sum = 1.f;
+      float pt[4] = {0.f, 0.f, 0.f, 0.f};   // KTAIL: softmax numerators of the tail keys (P V term added in the epilogue)
       if (warp_active) {
         // Columns [0, 32*nfull) need no key mask; the rest (< 48 columns) is handled 16 at a time with the mask.
-        const int nfull = p.N >> 5;
+        const int nk = KTAIL ? p.N - p.ktail : p.N;   // keys in the S tile
+        const int nfull = nk >> 5;
         uint32_t ra[32], rb[32];
+        // ---------------- key tail (N = 257: the S tile keeps 256 columns, so that two CTAs share an SM): scores of
+        // the last ktail keys from the Q / K rows in shared memory (swizzled as TMA wrote them), fp32
+        float st[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if constexpr (KTAIL) {
+          const uint8_t* qrow64 = stage + 2 * kv_bytes + t * Q_TILE_BYTES + r_in_tile * 128;
+          uint4 qv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) qv[j] = *reinterpret_cast<const uint4*>(qrow64 + ((j ^ (r_in_tile & 7)) << 4));
+          uint4 qx[2];
+          if constexpr (X16) {
+            const uint8_t* qrow16 = stage + 2 * kv_bytes + t * Q_TILE_BYTES + 128 * 128 + r_in_tile * 32;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) qx[j] = *reinterpret_cast<const uint4*>(qrow16 + ((j ^ ((r_in_tile >> 2) & 1)) << 4));
+          }
+          auto dot8 = [](const uint4& a, const uint4& b, float acc) {
+            const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fx = __bfloat1622float2(x[i]), fy = __bfloat1622float2(y[i]);
+              acc = fmaf(fx.x, fy.x, acc);
+              acc = fmaf(fx.y, fy.y, acc);
+            }
+            return acc;
+          };
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            if (tt < p.ktail) {
+              const int kr = nk + tt;
+              const uint8_t* krow = stage + kr * 128;
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                acc = dot8(qv[j], *reinterpret_cast<const uint4*>(krow + ((j ^ (kr & 7)) << 4)), acc);
+              if constexpr (X16) {
+                const uint8_t* krow16 = stage + kv64_bytes + kr * 32;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  acc = dot8(qx[j], *reinterpret_cast<const uint4*>(krow16 + ((j ^ ((kr >> 2) & 1)) << 4)), acc);
+              }
+              st[tt] = acc;
+            }
+          }
+        }
         // ---------------- pass 1: row max (4 independent chains; next chunk's tcgen05.ld in flight)
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #define ATT_MAX32(R)                                                    \
@@ -270,7 +339,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.N) m0 = fmaxf(m0, __uint_as_float(r16[j]));
+            if (c0 + j < nk) m0 = fmaxf(m0, __uint_as_float(r16[j]));
+        }
+        if constexpr (KTAIL) {
+          m0 = fmaxf(fmaxf(m0, st[0]), st[1]);
+          m1 = fmaxf(fmaxf(m1, st[2]), st[3]);
         }
         const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
         // ---------------- pass 2: p = exp2(s*c - max*c), row sum, P (bf16 pairs) -> TMEM over S
@@ -311,8 +384,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           uint32_t pk8[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float e0 = (c0 + j < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[j]), c, -mc)) : 0.f;
-            const float e1 = (c0 + j + 1 < p.N) ? fast_ex2(fmaf(__uint_as_float(r16[j + 1]), c, -mc)) : 0.f;
+            const float e0 = (c0 + j < nk) ? fast_ex2(fmaf(__uint_as_float(r16[j]), c, -mc)) : 0.f;
+            const float e1 = (c0 + j + 1 < nk) ? fast_ex2(fmaf(__uint_as_float(r16[j + 1]), c, -mc)) : 0.f;
             s0 += e0;
             s1 += e1;
             pk8[j >> 1] = pack_bf16x2(e0, e1);
@@ -323,6 +396,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #undef ATT_EXP32
 #undef ATT_EXP32_PLAIN
         sum = (s0 + s1) + (s2 + s3);
+        if constexpr (KTAIL) {
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            if (tt < p.ktail) {
+              pt[tt] = fast_ex2(fmaf(st[tt], c, -mc));
+              sum += pt[tt];
+            }
+          }
+        }
         tmem_st_wait();
       }
       tc_fence_before();
@@ -341,6 +423,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int hcol = 0; hcol < 2; ++hcol) {
             tmem_ld_32x32b_x32(t_lane + O_COL + 32 * hcol, r0);
             tmem_ld_wait();
+            if constexpr (KTAIL) {
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                if (tt >= p.ktail) break;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {   // 8 columns per 16-byte broadcast read
+                  const uint4 raw = *reinterpret_cast<const uint4*>(vtail + tt * (DH * 2) + hcol * 64 + q4 * 16);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(h2[i]);
+                    r0[8 * q4 + 2 * i] = __float_as_uint(fmaf(pt[tt], f.x, __uint_as_float(r0[8 * q4 + 2 * i])));
+                    r0[8 * q4 + 2 * i + 1] = __float_as_uint(fmaf(pt[tt], f.y, __uint_as_float(r0[8 * q4 + 2 * i + 1])));
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               ob[16 * hcol + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
@@ -351,6 +450,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int g = 0; g < DH / 16; ++g) {
             tmem_ld_32x32b_x16(t_lane + O_COL + 16 * g, r0);
             tmem_ld_wait();
+            if constexpr (KTAIL) {
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                if (tt >= p.ktail) break;
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                  const uint4 raw = *reinterpret_cast<const uint4*>(vtail + tt * (DH * 2) + g * 32 + q4 * 16);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(h2[i]);
+                    r0[8 * q4 + 2 * i] = __float_as_uint(fmaf(pt[tt], f.x, __uint_as_float(r0[8 * q4 + 2 * i])));
+                    r0[8 * q4 + 2 * i + 1] = __float_as_uint(fmaf(pt[tt], f.y, __uint_as_float(r0[8 * q4 + 2 * i + 1])));
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               ob[8 * g + j] = pack_bf16x2(__uint_as_float(r0[2 * j]) * inv, __uint_as_float(r0[2 * j + 1]) * inv);
@@ -376,6 +492,103 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+
+// Query tail: the last `qtail` (1..4) rows of every sequence when N = 128 a + qtail -- a whole 128-row tensor-core tile
+// for them would be 97..99 % padding (N = 257: a third of all tiles).  One CTA of 8 warps per (image, head, row):
+// warp w walks the key groups w, w + 8, ... (4 keys each) with an online softmax in fp32, lane l owns head dims
+// 2l, 2l + 1 (and 64 + 2l, 65 + 2l for l < 8 when dim_head = 80); the 8 partial (max, sum, acc) merge in shared memory.
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_qtail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int N, int H, int qtail,
+                       float c) {
+  constexpr int NW = 8;
+  constexpr bool X16 = DH == 80;
+  __shared__ float part[NW][4 + 96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x % qtail;
+  const int bh = blockIdx.x / qtail;
+  const int h = bh % H, b = bh / H;
+  const int I = H * DH;
+  const size_t ld = (size_t)3 * I;
+  const __nv_bfloat16* base = qkv + (size_t)b * N * ld + h * DH;
+  const int qrow = N - qtail + r;
+  const float2 q = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(base + (size_t)qrow * ld) + lane));
+  float2 qx = make_float2(0.f, 0.f);
+  if (X16 && lane < 8) qx = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(base + (size_t)qrow * ld + 64) + lane));
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int j = 4 * warp; j < N; j += 4 * NW) {
+    const int cnt = N - j < 4 ? N - j : 4;
+    float2 k[4], v[4], kx[4], vx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16* row = base + (size_t)(j + (i < cnt ? i : 0)) * ld;
+      k[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + I) + lane));
+      v[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + 2 * I) + lane));
+      if (X16 && lane < 8) {
+        kx[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + I + 64) + lane));
+        vx[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + 2 * I + 64) + lane));
+      } else {
+        kx[i] = vx[i] = make_float2(0.f, 0.f);
+      }
+    }
+    float sc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc[i] = q.x * k[i].x + q.y * k[i].y + qx.x * kx[i].x + qx.y * kx[i].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc[i] = i < cnt ? sc[i] * c : -INFINITY;   // log2 units; tail group: weight 0
+    const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+    const float f = fast_ex2(m - mn);
+    l *= f; a0 *= f; a1 *= f; a2 *= f; a3 *= f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float pj = fast_ex2(sc[i] - mn);
+      l += pj;
+      a0 = fmaf(pj, v[i].x, a0);
+      a1 = fmaf(pj, v[i].y, a1);
+      a2 = fmaf(pj, vx[i].x, a2);
+      a3 = fmaf(pj, vx[i].y, a3);
+    }
+    m = mn;
+  }
+  if (lane == 0) {
+    part[warp][0] = m;
+    part[warp][1] = l;
+  }
+  part[warp][4 + 2 * lane] = a0;
+  part[warp][5 + 2 * lane] = a1;
+  if (X16 && lane < 8) {
+    part[warp][68 + 2 * lane] = a2;
+    part[warp][69 + 2 * lane] = a3;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, part[w][0]);
+    float L = 0.f, A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float f = part[w][0] == -INFINITY ? 0.f : fast_ex2(part[w][0] - mm);   // warps without a key
+      L = fmaf(part[w][1], f, L);
+      A0 = fmaf(part[w][4 + 2 * lane], f, A0);
+      A1 = fmaf(part[w][5 + 2 * lane], f, A1);
+      if (X16 && lane < 8) {
+        A2 = fmaf(part[w][68 + 2 * lane], f, A2);
+        A3 = fmaf(part[w][69 + 2 * lane], f, A3);
+      }
+    }
+    const float inv = 1.0f / L;
+    __nv_bfloat16* orow = out + ((size_t)b * N + qrow) * I + h * DH;
+    *(reinterpret_cast<__nv_bfloat162*>(orow) + lane) = __floats2bfloat162_rn(A0 * inv, A1 * inv);
+    if (X16 && lane < 8) *(reinterpret_cast<__nv_bfloat162*>(orow + 64) + lane) = __floats2bfloat162_rn(A2 * inv, A3 * inv);
+  }
+}
+
 // test hooks (b200vit_debug_set): process-global, NOT part of the re-entrant API
 // 0 auto, 1 force the kernels below, 2 force the pipelined kernel (attention_pipe.cu) wherever N <= 224.  Auto is
 // currently the kernels below: at ViT-B/16 batch 512 they need 221 us per layer, the pipelined one 235 us
@@ -385,14 +598,15 @@ static std::atomic<int> g_attn_v_lbo{1024};  // V descriptor leading-dim byte of
 static std::atomic<int> g_attn_v_sbo{1024};  // V descriptor stride-dim byte offset
 static std::atomic<int> g_attn_v16_lbo{256};  // dim_head 80: the same two for the 16-wide V slab (bring-up probe)
 static std::atomic<int> g_attn_v16_sbo{256};
+static std::atomic<int> g_attn_tail{1};       // 1: key tail / query tail on the CUDA cores where they apply; 0: tiles only
 
 bool attention_pipe_eligible(int N, int dh);
 int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
                           cudaStream_t stream);
 
-template <int NWG, int STAGES, int TMEM_COLS, int DH>
+template <int NWG, int STAGES, int TMEM_COLS, int DH, bool KTAIL = false>
 static int launch_attention_t(const CUtensorMap* tm, const AttnParams& p, size_t smem_bytes, cudaStream_t stream) {
-  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS, DH>;
+  auto kern = attention_kernel<NWG, STAGES, TMEM_COLS, DH, KTAIL>;
   B200_ENSURE_SMEM(kern, smem_bytes);
   const int slots = num_sms() * (TMEM_COLS == 256 ? 2 : 1);
   const int grid = p.units < slots ? p.units : slots;
@@ -431,6 +645,7 @@ extern "C" int b200vit_debug_set(int key, int value) {
     case 13: attention_pipe_set_emul(value); return 0;
     case 14: g_attn_v16_lbo = value; return 0;
     case 15: g_attn_v16_sbo = value; return 0;
+    case 16: g_attn_tail = value; return 0;
     case 11: attention_varlen_set_mode(value); return 0;
     default: return B200VIT_ERR_INVALID;
   }
@@ -450,13 +665,20 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   AttnParams p{};
   p.B = B; p.N = N; p.H = H;
   p.I = H * dh;
-  p.KP = (N + 15) / 16 * 16;
+  // N = 256 + (1..4) (ViT-H/14 with its cls token: 257): a 272-column S tile would not fit twice into TMEM, so the tile
+  // keeps 256 keys (two CTAs per SM) and the softmax threads take the last keys themselves; N = 128 a + (1..4): the
+  // last rows get the CUDA-core kernel instead of a 128-row tile of their own.  g_attn_tail = 0 switches both off.
+  const bool tails = g_attn_tail.load() != 0;
+  p.ktail = (tails && N > 256 && N <= 260) ? N - 256 : 0;
+  const int qtail = (tails && N > 128 && N % 128 >= 1 && N % 128 <= 4) ? N % 128 : 0;
+  p.KP = (N - p.ktail + 15) / 16 * 16;
   // occupancy 2 (two single-warpgroup CTAs per SM, 256 TMEM columns each) whenever one region can hold S | P | O
   const bool occ2 = p.KP <= 256;
   const int nwg = occ2 ? 1 : ((N > 128 && p.KP <= 256) ? 2 : 1);
-  p.kv_boxes = (p.KP + 255) / 256;
-  p.kv_box_rows = ((p.KP + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
-  const int q_tiles = (N + 127) / 128;
+  const int kv_rows = p.ktail ? (N + 7) / 8 * 8 : p.KP;   // rows of K / V staged in shared memory
+  p.kv_boxes = (kv_rows + 255) / 256;
+  p.kv_box_rows = ((kv_rows + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
+  const int q_tiles = qtail ? N / 128 : (N + 127) / 128;
   p.rounds = (q_tiles + nwg - 1) / nwg;
   p.units = B * H * p.rounds;
   p.scale_log2e = scale * 1.4426950408889634f;
@@ -494,17 +716,31 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   const size_t kv16 = dh == 80 ? ((size_t)p.kv_boxes * p.kv_box_rows * 32 + 1023) / 1024 * 1024 : 0;
   const size_t kv_bytes = kv64 + kv16;
   const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * (128 * 128 + (dh == 80 ? 128 * 32 : 0));
-  auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024; };
+  auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024 + (p.ktail ? 1024 : 0); };
   // two K/V/Q stages when they fit (prefetch of the next unit), else one; the occupancy-2 variant uses one
   const int stages = (!occ2 && smem_for(2) <= 227 * 1024) ? 2 : 1;
   const size_t smem_bytes = smem_for(stages);
   B200_CHECK_ARG(smem_bytes <= 227 * 1024, "attention: N=%d needs %zu bytes of shared memory", N, smem_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (occ2 && smem_bytes <= 113 * 1024) return launch_attention<1, 1, 256>(tm, dh, p, smem_bytes, st);
-  if (nwg == 2) {
-    if (stages == 1) return launch_attention<2, 1>(tm, dh, p, smem_bytes, st);
-    return launch_attention<2, 2>(tm, dh, p, smem_bytes, st);
+  int rc;
+  if (p.ktail) {
+    B200_CHECK_ARG(occ2 && smem_bytes <= 113 * 1024, "attention: key-tail layout does not fit (N=%d)", N);
+    rc = dh == 80 ? launch_attention_t<1, 1, 256, 80, true>(tm, p, smem_bytes, st)
+                  : launch_attention_t<1, 1, 256, 64, true>(tm, p, smem_bytes, st);
+  } else if (occ2 && smem_bytes <= 113 * 1024) {
+    rc = launch_attention<1, 1, 256>(tm, dh, p, smem_bytes, st);
+  } else if (nwg == 2) {
+    rc = stages == 1 ? launch_attention<2, 1>(tm, dh, p, smem_bytes, st) : launch_attention<2, 2>(tm, dh, p, smem_bytes, st);
+  } else {
+    rc = stages == 1 ? launch_attention<1, 1>(tm, dh, p, smem_bytes, st) : launch_attention<1, 2>(tm, dh, p, smem_bytes, st);
   }
-  if (stages == 1) return launch_attention<1, 1>(tm, dh, p, smem_bytes, st);
-  return launch_attention<1, 2>(tm, dh, p, smem_bytes, st);
+  if (rc || !qtail) return rc;
+  const __nv_bfloat16* q16 = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  if (dh == 80)
+    attention_qtail_kernel<80><<<B * H * qtail, 256, 0, st>>>(q16, p.out, N, H, qtail, p.scale_log2e);
+  else
+    attention_qtail_kernel<64><<<B * H * qtail, 256, 0, st>>>(q16, p.out, N, H, qtail, p.scale_log2e);
+  B200_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
