@@ -121,9 +121,8 @@ int b200vit_rowstats_cast(const float* x, void* xb_bf16, float* stats, int M, in
  *   out[B*N, H*dh]   bf16 (merged heads, vit.py:63) = softmax(q k^T * scale) v          (vit.py:57-62)
  * One pass over the keys (N <= 512): S = QK^T and O = PV on tcgen05 with TMEM accumulators, fp32 softmax.
  * dh = 64, or 80 (canonical ViT-H/14): an 80-wide head is staged as a 64-wide + a 16-wide shared-memory slab.
- * N = 257 (ViT-H/14 with its cls token) and its neighbours: the score tile keeps 256 keys, so that two CTAs still
- * share an SM's 512 TMEM columns, and the softmax threads add the last 1..4 keys themselves; the last 1..4 query rows
- * of N = 128 a + (1..4) run in a second, CUDA-core launch instead of a 128-row tile of padding.
+ * N = 257 (ViT-H/14 with its cls token) .. 260: the score tile keeps 256 keys, so that two CTAs still share an SM's
+ * 512 TMEM columns, and the softmax threads add the last 1..4 keys themselves from shared memory.
  * (A software-pipelined variant for N <= 224, attention_pipe.cu, is built but only reachable through the test hook.)
  */
 int b200vit_attention(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
@@ -252,7 +251,7 @@ int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, float* x, con
  *           2 = pipelined 64-key blocks, two passes (exact max first)
  *   key 12: fp32-epilogue warps of the CTA-pair GEMM: 0 = auto (4 when K >= 2048, else 8), 4 / 8 = forced
  *   key 14 / 15: dim_head 80: LBO / SBO bytes of the 16-wide V slab descriptor (bring-up probe)
- *   key 16: b200vit_attention tails on the CUDA cores (N = 256 + 1..4 keys, N = 128 a + 1..4 rows): 1 = on (default), 0 = off
+ *   key 16: b200vit_attention key tail on the CUDA cores (N = 256 + 1..4 keys): 1 = on (default), 0 = off
  *   key 13: pipelined attention: 0 = all softmax exponentials on MUFU (default), 1 = half of them on the FMA pipe
  */
 int b200vit_debug_set(int key, int value);

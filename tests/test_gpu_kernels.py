@@ -307,18 +307,15 @@ def test_attention_dim_head_80(B, N, H):
 
 
 @pytest.mark.parametrize("dh", [64, 80])
-@pytest.mark.parametrize("B,N,H", [(3, 257, 4), (2, 258, 2), (2, 260, 3), (40, 257, 16), (3, 129, 2), (2, 132, 5),
-                                   (2, 385, 2), (2, 388, 1), (1, 261, 2), (300, 257, 2)])
-def test_attention_key_and_query_tails(B, N, H, dh):
+@pytest.mark.parametrize("B,N,H", [(3, 257, 4), (2, 258, 2), (2, 260, 3), (40, 257, 16), (1, 261, 2), (300, 257, 2)])
+def test_attention_key_tail(B, N, H, dh):
     """N = 256 + (1..4): the S tile keeps 256 keys (two CTAs per SM) and the softmax threads add the last keys' scores
-    and P V terms from shared memory; N = 128 a + (1..4): the last rows run in the CUDA-core kernel instead of a
-    128-row tile of their own.  Checked against the fp32 oracle with the tail keys made the dominant ones, and
-    against the tile-only path (test hook 16 = 0)."""
+    and P V terms from shared memory.  Checked against the fp32 oracle with the tail keys made the dominant ones, and
+    against the 272-column-tile path (test hook 16 = 0)."""
     torch.manual_seed(N + dh)
     I = H * dh
     qkv = torch.randn(B * N, 3 * I, device=DEV)
-    kview = qkv.view(B, N, 3, I)
-    kview[:, N - 2:, 1] *= 2.5                           # the last keys attract most of the attention
+    qkv.view(B, N, 3, I)[:, N - 2:, 1] *= 2.5            # the last keys attract most of the attention
     qkv = qkv.bfloat16()
     L = _lib.lib()
     outs = {}
@@ -326,17 +323,11 @@ def test_attention_key_and_query_tails(B, N, H, dh):
         out = torch.zeros(B * N, I, device=DEV, dtype=torch.bfloat16)
         L.b200vit_debug_set(16, tails)
         try:
-            _lib.reset_launch_count()
             _lib.attention(qkv, out, B, N, H, dh, dh ** -0.5)
             torch.cuda.synchronize()
-            launches = _lib.launch_count()
         finally:
             L.b200vit_debug_set(16, 1)
         outs[tails] = out.float().cpu()
-        if tails and N > 128 and 1 <= N % 128 <= 4:
-            assert launches == 2                         # tile kernel + query-tail kernel
-        else:
-            assert launches == 1
     q, k, v = qkv.float().cpu().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
     ref = (O.softmax_last((q @ k.transpose(-1, -2)) * dh ** -0.5) @ v).permute(0, 2, 1, 3).reshape(B * N, I)
     for tails in (1, 0):

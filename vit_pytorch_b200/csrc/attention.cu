@@ -493,102 +493,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 
-// Query tail: the last `qtail` (1..4) rows of every sequence when N = 128 a + qtail -- a whole 128-row tensor-core tile
-// for them would be 97..99 % padding (N = 257: a third of all tiles).  One CTA of 8 warps per (image, head, row):
-// warp w walks the key groups w, w + 8, ... (4 keys each) with an online softmax in fp32, lane l owns head dims
-// 2l, 2l + 1 (and 64 + 2l, 65 + 2l for l < 8 when dim_head = 80); the 8 partial (max, sum, acc) merge in shared memory.
-template <int DH>
-__global__ void __launch_bounds__(256)
-attention_qtail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int N, int H, int qtail,
-                       float c) {
-  constexpr int NW = 8;
-  constexpr bool X16 = DH == 80;
-  __shared__ float part[NW][4 + 96];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x % qtail;
-  const int bh = blockIdx.x / qtail;
-  const int h = bh % H, b = bh / H;
-  const int I = H * DH;
-  const size_t ld = (size_t)3 * I;
-  const __nv_bfloat16* base = qkv + (size_t)b * N * ld + h * DH;
-  const int qrow = N - qtail + r;
-  const float2 q = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(base + (size_t)qrow * ld) + lane));
-  float2 qx = make_float2(0.f, 0.f);
-  if (X16 && lane < 8) qx = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(base + (size_t)qrow * ld + 64) + lane));
-  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int j = 4 * warp; j < N; j += 4 * NW) {
-    const int cnt = N - j < 4 ? N - j : 4;
-    float2 k[4], v[4], kx[4], vx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat16* row = base + (size_t)(j + (i < cnt ? i : 0)) * ld;
-      k[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + I) + lane));
-      v[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + 2 * I) + lane));
-      if (X16 && lane < 8) {
-        kx[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + I + 64) + lane));
-        vx[i] = __bfloat1622float2(*(reinterpret_cast<const __nv_bfloat162*>(row + 2 * I + 64) + lane));
-      } else {
-        kx[i] = vx[i] = make_float2(0.f, 0.f);
-      }
-    }
-    float sc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sc[i] = q.x * k[i].x + q.y * k[i].y + qx.x * kx[i].x + qx.y * kx[i].y;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sc[i] = i < cnt ? sc[i] * c : -INFINITY;   // log2 units; tail group: weight 0
-    const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
-    const float f = fast_ex2(m - mn);
-    l *= f; a0 *= f; a1 *= f; a2 *= f; a3 *= f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float pj = fast_ex2(sc[i] - mn);
-      l += pj;
-      a0 = fmaf(pj, v[i].x, a0);
-      a1 = fmaf(pj, v[i].y, a1);
-      a2 = fmaf(pj, vx[i].x, a2);
-      a3 = fmaf(pj, vx[i].y, a3);
-    }
-    m = mn;
-  }
-  if (lane == 0) {
-    part[warp][0] = m;
-    part[warp][1] = l;
-  }
-  part[warp][4 + 2 * lane] = a0;
-  part[warp][5 + 2 * lane] = a1;
-  if (X16 && lane < 8) {
-    part[warp][68 + 2 * lane] = a2;
-    part[warp][69 + 2 * lane] = a3;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float mm = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, part[w][0]);
-    float L = 0.f, A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const float f = part[w][0] == -INFINITY ? 0.f : fast_ex2(part[w][0] - mm);   // warps without a key
-      L = fmaf(part[w][1], f, L);
-      A0 = fmaf(part[w][4 + 2 * lane], f, A0);
-      A1 = fmaf(part[w][5 + 2 * lane], f, A1);
-      if (X16 && lane < 8) {
-        A2 = fmaf(part[w][68 + 2 * lane], f, A2);
-        A3 = fmaf(part[w][69 + 2 * lane], f, A3);
-      }
-    }
-    const float inv = 1.0f / L;
-    __nv_bfloat16* orow = out + ((size_t)b * N + qrow) * I + h * DH;
-    *(reinterpret_cast<__nv_bfloat162*>(orow) + lane) = __floats2bfloat162_rn(A0 * inv, A1 * inv);
-    if (X16 && lane < 8) *(reinterpret_cast<__nv_bfloat162*>(orow + 64) + lane) = __floats2bfloat162_rn(A2 * inv, A3 * inv);
-  }
-}
-
 // test hooks (b200vit_debug_set): process-global, NOT part of the re-entrant API
 // 0 auto, 1 force the kernels below, 2 force the pipelined kernel (attention_pipe.cu) wherever N <= 224.  Auto is
 // currently the kernels below: at ViT-B/16 batch 512 they need 221 us per layer, the pipelined one 235 us
@@ -598,7 +502,7 @@ static std::atomic<int> g_attn_v_lbo{1024};  // V descriptor leading-dim byte of
 static std::atomic<int> g_attn_v_sbo{1024};  // V descriptor stride-dim byte offset
 static std::atomic<int> g_attn_v16_lbo{256};  // dim_head 80: the same two for the 16-wide V slab (bring-up probe)
 static std::atomic<int> g_attn_v16_sbo{256};
-static std::atomic<int> g_attn_tail{1};       // 1: key tail / query tail on the CUDA cores where they apply; 0: tiles only
+static std::atomic<int> g_attn_tail{1};       // 1: key tail (N = 257..260) on the CUDA cores; 0: 272-column tiles
 
 bool attention_pipe_eligible(int N, int dh);
 int launch_attention_pipe(const void* qkv, void* out, int B, int N, int H, float scale, unsigned v_lbo, unsigned v_sbo,
@@ -666,11 +570,10 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   p.B = B; p.N = N; p.H = H;
   p.I = H * dh;
   // N = 256 + (1..4) (ViT-H/14 with its cls token: 257): a 272-column S tile would not fit twice into TMEM, so the tile
-  // keeps 256 keys (two CTAs per SM) and the softmax threads take the last keys themselves; N = 128 a + (1..4): the
-  // last rows get the CUDA-core kernel instead of a 128-row tile of their own.  g_attn_tail = 0 switches both off.
-  const bool tails = g_attn_tail.load() != 0;
-  p.ktail = (tails && N > 256 && N <= 260) ? N - 256 : 0;
-  const int qtail = (tails && N > 128 && N % 128 >= 1 && N % 128 <= 4) ? N % 128 : 0;
+  // keeps 256 keys (two CTAs per SM) and the softmax threads take the last keys themselves (g_attn_tail = 0: off).
+  // (A CUDA-core kernel for the 257th QUERY row instead of a third 128-row tile was measured too: 58 us per launch at
+  // batch 128 x 16 heads against 50 us for the tile -- not kept.)
+  p.ktail = (g_attn_tail.load() != 0 && N > 256 && N <= 260) ? N - 256 : 0;
   p.KP = (N - p.ktail + 15) / 16 * 16;
   // occupancy 2 (two single-warpgroup CTAs per SM, 256 TMEM columns each) whenever one region can hold S | P | O
   const bool occ2 = p.KP <= 256;
@@ -678,7 +581,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   const int kv_rows = p.ktail ? (N + 7) / 8 * 8 : p.KP;   // rows of K / V staged in shared memory
   p.kv_boxes = (kv_rows + 255) / 256;
   p.kv_box_rows = ((kv_rows + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
-  const int q_tiles = qtail ? N / 128 : (N + 127) / 128;
+  const int q_tiles = (N + 127) / 128;
   p.rounds = (q_tiles + nwg - 1) / nwg;
   p.units = B * H * p.rounds;
   p.scale_log2e = scale * 1.4426950408889634f;
@@ -734,13 +637,5 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   } else {
     rc = stages == 1 ? launch_attention<1, 1>(tm, dh, p, smem_bytes, st) : launch_attention<1, 2>(tm, dh, p, smem_bytes, st);
   }
-  if (rc || !qtail) return rc;
-  const __nv_bfloat16* q16 = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  if (dh == 80)
-    attention_qtail_kernel<80><<<B * H * qtail, 256, 0, st>>>(q16, p.out, N, H, qtail, p.scale_log2e);
-  else
-    attention_qtail_kernel<64><<<B * H * qtail, 256, 0, st>>>(q16, p.out, N, H, qtail, p.scale_log2e);
-  B200_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return rc;
 }
