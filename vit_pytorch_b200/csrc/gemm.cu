@@ -401,10 +401,7 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.col_s = col_s;
   p.stats_out = stats_out;
 
-  // 128 x 256 tiles unless they would leave most SMs without one (small batches: M = 197 .. 1000 rows): then
-  // 128 x 128 tiles double the number of CTAs that stream the weight matrix
-  const long long tiles256 = (long long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
-  const bool wide = N > 128 && tiles256 * 2 >= num_sms();
+  const bool wide = N > 128;
   const uint32_t block_n = wide ? 256 : 128;
   CUtensorMap tmA, tmB;
   {
