@@ -191,7 +191,7 @@ int ensure_dyn_smem(const void* kernel, size_t bytes) {
 extern "C" {
 
 const char* b200vit_last_error(void) { return b200::g_err; }
-int b200vit_version(void) { return 200; }  /* round 2 */
+int b200vit_version(void) { return 210; }  /* round 2, final kernels */
 int64_t b200vit_launch_count(void) { return b200::g_launches.load(); }
 void b200vit_reset_launch_count(void) { b200::g_launches.store(0); }
 
