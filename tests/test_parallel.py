@@ -64,3 +64,53 @@ def test_two_rank_gloo_all_gather(total):
 def test_all_gather_without_process_group_is_identity():
     x = torch.randn(3, 4)
     assert all_gather_logits(x) is x
+
+
+def test_balanced_bounds_minimise_the_largest_slice():
+    from vit_pytorch_b200.parallel import balanced_bounds
+    import itertools
+    import random
+    rnd = random.Random(0)
+    for n, world in ((1, 4), (5, 2), (9, 3), (12, 4), (7, 8)):
+        costs = [rnd.randint(1, 100) ** 2 for _ in range(n)]
+        b = balanced_bounds(costs, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        got = max(sum(costs[lo:hi]) for lo, hi in b)
+        # brute force over all contiguous partitions into at most `world` slices
+        best = min(max(sum(costs[a:c]) for a, c in zip((0,) + cuts, cuts + (n,)))
+                   for k in range(min(world, n)) for cuts in itertools.combinations(range(1, n), k))
+        assert got <= best * (1 + 1e-6), (costs, world, got, best)
+    assert balanced_bounds([], 3) == [(0, 0)] * 3
+
+
+def _navit_worker(rank, world, port, ret):
+    from vit_pytorch_b200.na_vit import NaViT
+    from vit_pytorch_b200.parallel import navit_data_parallel_forward
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    model = NaViT(image_size=32, patch_size=8, num_classes=5, dim=32, depth=1, heads=2, mlp_dim=32, dim_head=16).eval()
+    g = torch.Generator().manual_seed(3)
+    sizes = [(32, 32), (8, 8), (8, 16), (16, 8), (8, 8), (24, 32), (8, 8)]     # one large image first: 1 | 6 split
+    imgs = [torch.randn(3, h, w, generator=g) for h, w in sizes]
+    out = navit_data_parallel_forward(model, imgs)
+    full = model(imgs)
+    ret[rank] = bool(out.shape == full.shape and torch.allclose(out, full, atol=1e-5))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_navit_balanced_split():
+    """Variable-resolution images are split by per-layer work, not by count; logits come back in input order."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_navit_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret[r] for r in range(world))
