@@ -40,7 +40,8 @@ __host__ __device__ inline int att_kv_bytes(int kv_boxes, int kv_box_rows) { ret
 // TWO independent CTAs per SM, each with one softmax warpgroup -- while one CTA waits for its MMAs or loads, the
 // other one's softmax keeps the MUFU / issue slots busy.
 // (The round-1 experiments -- FMA-pipe exp2, split PV accumulation, skipped row max, 8 warps per tile, globaltimer
-// traces -- are recorded in profiles/r01*; their code is gone.  Shapes with N <= 224 run attention_pipe.cu instead.)
+// traces -- are recorded in profiles/r01*; their code is gone.  attention_pipe.cu, a software-pipelined variant for
+// N <= 224, is reachable through the test hook only: it measured 6 % slower, profiles/r02_attention.md.)
 //
 // DH = 64 or 80 (canonical ViT-H/14, reference vit.py:86 `dim_head`).  128-byte swizzled TMA boxes are 64 bf16 wide, so
 // an 80-wide head is staged as a 64-wide slab plus a 16-wide slab (32-byte rows, 32-byte swizzle): Q K^T gets a

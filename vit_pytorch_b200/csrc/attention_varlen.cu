@@ -4,8 +4,10 @@
 //   out[T, H*64]   bf16 :  out_s = softmax(q_s k_s^T * scale) v_s        -- tokens of different sequences never mix
 //
 // This is the block-diagonal ("same image id") attention of NaViT (reference na_vit.py:335-337,161-166) in its
-// mask-free varlen form, and the long-sequence path of ViT (N > 512).  Work unit = (sequence, head, 128-row query
-// tile); keys are walked in blocks of 128:
+// mask-free varlen form, and the long-sequence path of ViT (N > 512).  THREE kernels live in this file; the default is
+// attention_varlen2_kernel<.., ONLINE = true> further down (64-key blocks, three score buffers, ONE pass over the keys
+// with a lazily moved reference max).  First, the original serial kernel (test hook 11 = 1).  Work unit = (sequence,
+// head, 128-row query tile); keys are walked in blocks of 128:
 //   phase 1 (only if the sequence has more than one key block): S_b = Q K_b^T for every block, softmax warps keep the
 //           running row max -- the FINAL max is known before any exponential is taken, so
 //   phase 2 needs no online rescaling: S_b again, P_b = exp2((S_b - max) * scale*log2e) as bf16 back into TMEM
@@ -290,7 +292,10 @@ attention_varlen_kernel(const __grid_constant__ CUtensorMap tm, const AttnVarlen
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Pipelined variant (the default): the same two-phase algorithm on key blocks of 64 with THREE score buffers, so that
+// Pipelined variant: key blocks of 64 with THREE score buffers.  ONLINE = false (test hook 11 = 2): the same two-phase
+// algorithm as above (exact max first).  ONLINE = true (the default): one pass -- exponentials are taken against a
+// per-row reference max that moves only when a block exceeds it by 2^24, which rescales O in TMEM.
+// In both, the three buffers mean that
 // Q K^T of the next two blocks is issued before the softmax warps have finished block b and before P_b V_b has
 // completed -- the MMA round trips (issue -> commit -> mbarrier -> wake-up, ~0.7 us each) that serialised every
 // 128-key step of the kernel above overlap with the exponentials.  TMEM: S|P buffers at [0,64), [64,128) and
