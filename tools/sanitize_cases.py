@@ -40,6 +40,11 @@ if "attention" in which:
         o = torch.zeros(B * N, H * 64, device=dev, dtype=torch.bfloat16)
         _lib.attention(qkv, o, B, N, H, 64, 0.125)
     L.b200vit_debug_set(1, 0)
+    for dh, (B, N, H) in ((64, (3, 257, 2)), (80, (2, 258, 2)), (64, (150, 257, 2)), (80, (2, 197, 3))):
+        # key tail (N = 257..260: 256-key score tile + the last keys from shared memory), both head widths
+        qkv = torch.randn(B * N, 3 * H * dh, device=dev).bfloat16()
+        o = torch.zeros(B * N, H * dh, device=dev, dtype=torch.bfloat16)
+        _lib.attention(qkv, o, B, N, H, dh, dh ** -0.5)
     for mode in (0, 1, 2):
         L.b200vit_debug_set(11, mode)
         lengths = [197, 1, 130, 300, 64]

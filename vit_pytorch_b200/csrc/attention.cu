@@ -74,7 +74,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* o_full = p_ready + NWG;
   uint64_t* o_free = o_full + NWG;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + NWG);
-  uint8_t* vtail = reinterpret_cast<uint8_t*>(bars) + 256;   // KTAIL: [4][DH] bf16, V rows of the tail keys (host adds 1 KB)
+  uint8_t* vtail_base = reinterpret_cast<uint8_t*>(bars) + 256;   // KTAIL: 2 x [4][DH] bf16, V rows of the tail keys (host adds 2 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -242,11 +242,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&s_full[t], up);
       tc_fence_after();
       const uint8_t* stage = smem + (it % STAGES) * stage_bytes;
+      uint8_t* vtail = vtail_base + (it & 1) * (4 * DH * 2);
       if constexpr (KTAIL) {
         // the tail keys' V rows leave the stage before P V is released (after it the producer refills the stage):
         // un-swizzled copy into a scratch area every softmax thread reads in the epilogue.  All four warps pass here
-        // (also the ones without valid rows); the previous unit's readers are done (they have arrived on o_free,
-        // which S of this unit waited for).
+        // (also the ones without valid rows).  Two scratch areas alternate, so the readers of unit it - 2 and this
+        // write are separated by the bar.sync of unit it - 1 (they are ordered through o_free -> S MMA -> s_full as
+        // well, but that chain is invisible to racecheck).
         mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);     // TMA bytes visible to THIS thread
         if (quad == 0) {
           const int nk0 = p.N - p.ktail;
@@ -620,7 +622,7 @@ extern "C" int b200vit_attention(const void* qkv, void* out, int B, int N, int H
   const size_t kv16 = dh == 80 ? ((size_t)p.kv_boxes * p.kv_box_rows * 32 + 1023) / 1024 * 1024 : 0;
   const size_t kv_bytes = kv64 + kv16;
   const size_t stage_bytes = 2 * kv_bytes + (size_t)nwg * (128 * 128 + (dh == 80 ? 128 * 32 : 0));
-  auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024 + (p.ktail ? 1024 : 0); };
+  auto smem_for = [&](int st) { return st * stage_bytes + (2 * st + 4 * nwg) * 8 + 16 + 1024 + (p.ktail ? 2048 : 0); };
   // two K/V/Q stages when they fit (prefetch of the next unit), else one; the occupancy-2 variant uses one
   const int stages = (!occ2 && smem_for(2) <= 227 * 1024) ? 2 : 1;
   const size_t smem_bytes = smem_for(stages);
