@@ -302,3 +302,76 @@ def test_one_call_encoder_equals_the_per_kernel_host_loop(case, monkeypatch):
         counts[loop] = _lib.launch_count()
     assert torch.equal(outs["c"], outs["python"])
     assert counts["c"] == counts["python"] > 0
+
+
+@pytest.mark.parametrize("mode", ["fold", "exact"])
+def test_trained_like_statistics_stay_below_the_bf16_floor(mode, monkeypatch):
+    """Random-init weights are benign; trained ViTs are not: a few residual channels carry massive activations, the
+    residual stream has a common offset (row mean several sigma away from zero -- the case where normalising an
+    already bf16-rounded row, as the LN-fold path AND the reference's bf16 module do, loses digits), LayerNorm gains
+    are spread out and attention is peaky.  Expectation: the module's own fp32 PyTorch graph (equal to the reference,
+    tests/test_dropin.py); pass criterion: no worse than the same graph in bf16 (= the reference's bf16 forward)."""
+    monkeypatch.setenv("B200VIT_LN_MODE", mode)
+    torch.manual_seed(0)
+    kw = dict(image_size=224, patch_size=16, num_classes=100, dim=384, depth=6, heads=6, mlp_dim=1536)
+    m = ViT(**kw).eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() == 1 and name.endswith("weight"):                        # LayerNorm gains: 0.4 .. 2.5
+                p.copy_(torch.exp(0.45 * torch.randn(p.shape, generator=g)))
+            elif p.dim() == 1 and "norm" in name and name.endswith("bias"):
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+        for i, (attn, ff) in enumerate(m.transformer.layers):
+            attn.to_qkv.weight[: 2 * 384] *= 2.5                                 # q, k: peaky softmax
+            fc2 = ff.net[4] if hasattr(ff, "net") else None
+            if i < 2:
+                for c in (7, 100, 250):                                          # massive-activation channels
+                    fc2.weight[c] *= 20.0
+                    fc2.bias[c] += 8.0
+                fc2.bias += 1.5                                                  # common offset of the whole stream
+        for p in m.parameters():
+            p.copy_(p.bfloat16().float())
+    img = torch.randn(4, 3, 224, 224, generator=g).bfloat16()
+    m = m.to(DEV)
+    with torch.inference_mode():
+        ref = m.forward_eager(img.to(DEV).float()).float().cpu()
+        # how hostile the stream is: row mean / row std of the residual stream entering the last layer
+        x = m.to_patch_embedding(img.to(DEV).float())
+        x = torch.cat((m.cls_token.unsqueeze(0).expand(4, -1, -1), x), dim=1) + m.pos_embedding[:197]
+        for attn, ff in list(m.transformer.layers)[:-1]:
+            x = attn(x) + x
+            x = ff(x) + x
+        ratio = (x.mean(-1).abs() / x.std(-1)).mean().item()
+        peak = x.abs().max().item()
+        mb = m.bfloat16()
+        floor = mb.forward_eager(img.to(DEV)).float().cpu()
+        assert mb.fused_reason(img.to(DEV)) is None
+        out = mb(img.to(DEV)).float().cpu()
+    d, f = (out - ref).abs(), (floor - ref).abs()
+    print(f"trained-like [{mode}]: |row mean| / row std {ratio:.2f}, max |x| {peak:.0f}, logits |max| {ref.abs().max():.2f}; "
+          f"fused max {d.max():.4f} mean {d.mean():.5f}; bf16 graph max {f.max():.4f} mean {f.mean():.5f}")
+    assert torch.isfinite(out).all()
+    assert d.mean() <= f.mean() * 1.05 + 1e-4 and d.max() <= f.max() * 1.5 + 1e-3
+
+
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_split_k_latency_mode_matches_the_default(B, monkeypatch):
+    """B200VIT_SPLITK=1: batches of <= 1024 token rows split K of the encoder GEMMs over more CTAs.  Same logits up to
+    the association of the K sums (compared with the default path and with the fp32 oracle through the golden)."""
+    kwargs = dict(image_size=224, patch_size=16, num_classes=1000, dim=768, depth=12, heads=12, mlp_dim=3072)
+    torch.manual_seed(0)
+    m = ViT(**kwargs).eval().to(DEV, torch.bfloat16)
+    torch.manual_seed(1)
+    img = torch.randn(B, 3, 224, 224, device=DEV).bfloat16()
+    outs, launches = {}, {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("B200VIT_SPLITK", flag)
+        _lib.reset_launch_count()
+        with torch.inference_mode():
+            outs[flag] = m(img).float().cpu()
+        launches[flag] = _lib.launch_count()
+    assert launches["1"] == launches["0"] + 4 * 12                       # four GEMMs per layer became two launches
+    d = (outs["1"] - outs["0"]).abs()
+    print(f"split-K B={B}: max |delta logit| {d.max():.5f} mean {d.mean():.6f}")
+    assert d.max() < 1e-2 and d.mean() < 1.5e-3
