@@ -61,16 +61,6 @@ int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
                       int64_t ldo, const float* bias, const float* resid, const float* ln_sums, int ln_parts,
                       float ln_eps, const float* col_s, float* stats_out, int M, int N, int K, int flags,
                       void* stream);
-/*
- * The same GEMM with a caller-owned scratch buffer: when M is small (M <= 1024 with fewer output tiles than half the
- * SMs -- batch 1..4 of ViT-B/16) and workspace_bytes >= splits * M * ldo * 4, K is split over up to 16 groups of CTAs
- * that write raw fp32 partials into the workspace, and a row kernel adds them (in index order: deterministic) and
- * applies the epilogue.  Same arguments and results up to the association of the K sum; workspace NULL = never split.
- */
-int b200vit_gemm_bf16_ws(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16, float* out_f32,
-                         int64_t ldo, const float* bias, const float* resid, const float* ln_sums, int ln_parts,
-                         float ln_eps, const float* col_s, float* stats_out, int M, int N, int K, int flags,
-                         void* workspace, int64_t workspace_bytes, void* stream);
 /* number of per-row partial statistics an EPI_STATS GEMM with N output columns writes */
 int b200vit_stats_parts(int N);
 
@@ -245,8 +235,6 @@ typedef struct b200vit_layer {
 typedef struct b200vit_encoder_ws {
   void *xb, *qkv, *o, *h;
   float *stats_in, *stats_a, *stats_b;
-  void* splitk;             /* optional scratch of b200vit_gemm_bf16_ws (small batches), may be NULL */
-  int64_t splitk_bytes;
 } b200vit_encoder_ws;
 int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, float* x, const b200vit_encoder_ws* ws, int B, int N,
                            int D, int heads, int dh, int hidden, float scale, int primed,

@@ -54,11 +54,11 @@ def test_bad_arguments_return_error_codes(lib):
     rc = lib.b200vit_encoder_blocks(layers, 1, ctypes.c_void_p(256), ctypes.byref(ws), 1, 16, 64, 1, 64, 128, 0.125, 0,
                                     None, None, 0, None)
     assert rc == -1 and b"workspace" in lib.b200vit_last_error()
-    full = _lib.EncoderWs(*([256] * 7), None, 0)
+    full = _lib.EncoderWs(*([256] * 7))
     rc = lib.b200vit_encoder_blocks(layers, 1, ctypes.c_void_p(256), ctypes.byref(full), 1, 600, 64, 1, 64, 128, 0.125,
                                     1, None, None, 0, None)
     assert rc == -1 and b"varlen" in lib.b200vit_last_error()
-    assert ctypes.sizeof(_lib.Layer) == 11 * 8 + 8 and ctypes.sizeof(_lib.EncoderWs) == 9 * 8   # as the C structs
+    assert ctypes.sizeof(_lib.Layer) == 11 * 8 + 8 and ctypes.sizeof(_lib.EncoderWs) == 7 * 8   # as the C structs
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

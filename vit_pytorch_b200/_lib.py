@@ -31,7 +31,7 @@ SYMBOLS = [
     "b200vit_stats_parts", "b200vit_attention_varlen", "b200vit_qk_rmsnorm", "b200vit_attn_pool",
     "b200vit_patchify_varlen_ln", "b200vit_rmsnorm_heads", "b200vit_embed_varlen",
     "b200vit_gemm_headnorm_bf16", "b200vit_layernorm_heads", "b200vit_patch_stats", "b200vit_patch_embed_tma",
-    "b200vit_encoder_blocks", "b200vit_gemm_bf16_ws",
+    "b200vit_encoder_blocks",
 ]
 
 
@@ -46,8 +46,7 @@ class Layer(C.Structure):
 class EncoderWs(C.Structure):
     """struct b200vit_encoder_ws: scratch buffers of b200vit_encoder_blocks."""
     _fields_ = [("xb", C.c_void_p), ("qkv", C.c_void_p), ("o", C.c_void_p), ("h", C.c_void_p),
-                ("stats_in", C.c_void_p), ("stats_a", C.c_void_p), ("stats_b", C.c_void_p),
-                ("splitk", C.c_void_p), ("splitk_bytes", C.c_int64)]
+                ("stats_in", C.c_void_p), ("stats_a", C.c_void_p), ("stats_b", C.c_void_p)]
 
 _lib: Optional[C.CDLL] = None
 
@@ -77,9 +76,6 @@ def lib() -> C.CDLL:
     L.b200vit_gemm_bf16.restype = i32
     L.b200vit_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
                                     vp]
-    L.b200vit_gemm_bf16_ws.restype = i32
-    L.b200vit_gemm_bf16_ws.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, f32, vp, vp, i32, i32, i32, i32,
-                                       vp, i64, vp]
     L.b200vit_gemm_headnorm_bf16.restype = i32
     L.b200vit_gemm_headnorm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, f32, vp, vp, i32, i32, f32, i32,
                                              i32, i32, i32, vp]
@@ -223,11 +219,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
          out_f32: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, gelu: bool = False, ln_sums: Optional[torch.Tensor] = None,
          ln_eps: float = 1e-5, col_s: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
-         n: Optional[int] = None, k: Optional[int] = None, workspace: Optional[torch.Tensor] = None) -> None:
+         n: Optional[int] = None, k: Optional[int] = None) -> None:
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16 row-major (last stride 1).
-
-    workspace: optional scratch (any dtype, contiguous) -- small-M problems then split K over more CTAs
-    (b200vit_gemm_bf16_ws); results differ from the un-split kernel only in the association of the K sum.
 
     ln_sums: [M, parts, 2] (or [M, 2]) partial row sums of `a`; stats_out: [M, stats_parts(N), 2], fully overwritten."""
     _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
@@ -259,12 +252,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out_bf16: Optional[torch.Tensor] =
         flags |= EPI_STATS
         assert stats_out.is_contiguous() and tuple(stats_out.shape) == (M, stats_parts(N), 2), \
             f"stats_out must be [M, {stats_parts(N)}, 2]"
-    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
     with _Timed("gemm", M=M, N=N, K=K, flags=flags, flops=2.0 * M * N * K):
-        rc = lib().b200vit_gemm_bf16_ws(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
-                                        out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), ln_parts,
-                                        float(ln_eps), _ptr(col_s), _ptr(stats_out), M, N, K, flags, _ptr(workspace),
-                                        ws_bytes, _stream())
+        rc = lib().b200vit_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out_bf16), _ptr(out_f32),
+                                     out.stride(0), _ptr(bias), _ptr(resid), _ptr(ln_sums), ln_parts, float(ln_eps),
+                                     _ptr(col_s), _ptr(stats_out), M, N, K, flags, _stream())
     _check(rc, "b200vit_gemm_bf16")
 
 

@@ -11,7 +11,7 @@ using namespace b200;
 
 // the ctypes mirror (vit_pytorch_b200/_lib.py: Layer, EncoderWs) is laid out by hand: pin the C side
 static_assert(sizeof(b200vit_layer) == 11 * sizeof(void*) + 2 * sizeof(float), "b200vit_layer layout");
-static_assert(sizeof(b200vit_encoder_ws) == 8 * sizeof(void*) + sizeof(int64_t), "b200vit_encoder_ws layout");
+static_assert(sizeof(b200vit_encoder_ws) == 7 * sizeof(void*), "b200vit_encoder_ws layout");
 
 extern "C" int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, float* x, const b200vit_encoder_ws* ws,
                                       int B, int N, int D, int heads, int dh, int hidden, float scale, int primed,
@@ -42,9 +42,8 @@ extern "C" int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, fl
                                       L.qkv_s, L.qk_gamma, 2 * heads, dh, 0.f, M, 3 * I, D,
                                       B200VIT_EPI_BIAS | B200VIT_EPI_LNFOLD, stream);
     else
-      rc = b200vit_gemm_bf16_ws(ws->xb, D, L.qkv_wg, D, ws->qkv, nullptr, 3 * I, L.qkv_t, nullptr, sums, sum_parts,
-                                L.ln1_eps, L.qkv_s, nullptr, M, 3 * I, D, B200VIT_EPI_BIAS | B200VIT_EPI_LNFOLD,
-                                ws->splitk, ws->splitk_bytes, stream);
+      rc = b200vit_gemm_bf16(ws->xb, D, L.qkv_wg, D, ws->qkv, nullptr, 3 * I, L.qkv_t, nullptr, sums, sum_parts,
+                             L.ln1_eps, L.qkv_s, nullptr, M, 3 * I, D, B200VIT_EPI_BIAS | B200VIT_EPI_LNFOLD, stream);
     if (rc) return rc;
     // softmax(q k^T * scale) v, heads merged   (vit.py:55-63)
     if (N <= 512)
@@ -54,21 +53,18 @@ extern "C" int b200vit_encoder_blocks(const b200vit_layer* layers, int depth, fl
                                     scale, stream);
     if (rc) return rc;
     // to_out + residual   (vit.py:64,80)
-    rc = b200vit_gemm_bf16_ws(ws->o, I, L.out_w, I, ws->xb, x, D, L.out_b, x, nullptr, 0, 0.f, nullptr, ws->stats_b, M,
-                              D, I, (L.out_b ? B200VIT_EPI_BIAS : 0) | B200VIT_EPI_RESIDUAL | B200VIT_EPI_STATS,
-                              ws->splitk, ws->splitk_bytes, stream);
+    rc = b200vit_gemm_bf16(ws->o, I, L.out_w, I, ws->xb, x, D, L.out_b, x, nullptr, 0, 0.f, nullptr, ws->stats_b, M, D,
+                           I, (L.out_b ? B200VIT_EPI_BIAS : 0) | B200VIT_EPI_RESIDUAL | B200VIT_EPI_STATS, stream);
     if (rc) return rc;
     // LN -> Linear -> GELU   (vit.py:19-21)
-    rc = b200vit_gemm_bf16_ws(ws->xb, D, L.fc1_wg, D, ws->h, nullptr, hidden, L.fc1_t, nullptr, ws->stats_b, parts,
-                              L.ln2_eps, L.fc1_s, nullptr, M, hidden, D,
-                              B200VIT_EPI_BIAS | B200VIT_EPI_GELU | B200VIT_EPI_LNFOLD, ws->splitk, ws->splitk_bytes,
-                              stream);
+    rc = b200vit_gemm_bf16(ws->xb, D, L.fc1_wg, D, ws->h, nullptr, hidden, L.fc1_t, nullptr, ws->stats_b, parts,
+                           L.ln2_eps, L.fc1_s, nullptr, M, hidden, D,
+                           B200VIT_EPI_BIAS | B200VIT_EPI_GELU | B200VIT_EPI_LNFOLD, stream);
     if (rc) return rc;
     // Linear + residual   (vit.py:23,81)
-    rc = b200vit_gemm_bf16_ws(ws->h, hidden, L.fc2_w, hidden, ws->xb, x, D, L.fc2_b, x, nullptr, 0, 0.f, nullptr,
-                              ws->stats_a, M, D, hidden,
-                              (L.fc2_b ? B200VIT_EPI_BIAS : 0) | B200VIT_EPI_RESIDUAL | B200VIT_EPI_STATS, ws->splitk,
-                              ws->splitk_bytes, stream);
+    rc = b200vit_gemm_bf16(ws->h, hidden, L.fc2_w, hidden, ws->xb, x, D, L.fc2_b, x, nullptr, 0, 0.f, nullptr,
+                           ws->stats_a, M, D, hidden,
+                           (L.fc2_b ? B200VIT_EPI_BIAS : 0) | B200VIT_EPI_RESIDUAL | B200VIT_EPI_STATS, stream);
     if (rc) return rc;
   }
   return 0;

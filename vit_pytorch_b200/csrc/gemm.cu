@@ -44,12 +44,6 @@ struct GemmParams {
   // lands on its own 128-byte shared-memory row (measured: tools/patch_tma_probe.py), so the four pixel rows of a
   // k block cannot share one operand row; they are loaded as four boxes into four 16 KB slabs, each a K-major
   // operand of which the tensor core reads the first 16 k (one tcgen05.mma k-step per slab).
-  // Split-K (small M: too few output tiles to occupy the SMs): tile index = split * (m tiles * n tiles) + ..., split
-  // s accumulates k blocks [s * kb_per_split, ...) and writes its RAW fp32 partial to out_f32 + s * split_stride
-  // (flags must be 0); b200vit_splitk_epilogue_kernel adds the partials up in index order and applies the epilogue.
-  int splits;               // 0 / 1: off
-  int kb_per_split;
-  long long split_stride;   // elements
   int patch;
   int patch_ght;            // patch rows per tile
   int patch_tiles_per_img;  // gh / patch_ght
@@ -112,18 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
-  const int splits = p.splits > 1 ? p.splits : 1;
-  const int num_tiles = tiles_mn * splits;
-  // (split, m, n) of a tile and its k-block range
-  auto decode = [&](int tile, int& sp, int& m_blk, int& n_blk, int& kb0, int& kb1) {
-    sp = tile / tiles_mn;
-    const int rem = tile - sp * tiles_mn;
-    m_blk = rem / p.num_n_tiles;
-    n_blk = rem % p.num_n_tiles;
-    kb0 = splits > 1 ? sp * p.kb_per_split : 0;
-    kb1 = splits > 1 ? (kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks) : p.num_k_blocks;
-  };
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -131,9 +114,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int sp, m_blk, n_blk, kb0, kb1;
-        decode(tile, sp, m_blk, n_blk, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
@@ -169,9 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        int sp, m_blk, n_blk, kb0, kb1;
-        decode(tile, sp, m_blk, n_blk, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -183,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
             // (patch mode: the k-th 16 k of A are the first 32 bytes of the rows of slab k)
             const uint64_t ad = PATCH ? make_smem_desc_sw128(sa + k * L::A_SLAB, 16, 1024) : adesc + 2 * k;
-            umma_ss(d_tmem, ad, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, ad, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) {
@@ -209,9 +190,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int sp, m_blk, n_blk, kb0, kb1;
-      decode(tile, sp, m_blk, n_blk, kb0, kb1);
-      float* const out_f32 = p.out_f32 ? p.out_f32 + (size_t)sp * p.split_stride : nullptr;
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile % p.num_n_tiles;
       const int row = m_blk * p.rows_per_tile + quad * 32 + lane;
       const bool row_ok = row < p.M && quad * 32 + lane < p.rows_per_tile;
       float mu = 0.f, rstd = 1.f;
@@ -281,8 +261,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
                 v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
               }
-              if (out_f32) {
-                float* op = out_f32 + (size_t)row * p.ldo + col;
+              if (p.out_f32) {
+                float* op = p.out_f32 + (size_t)row * p.ldo + col;
                 *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
               }
@@ -314,7 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (flags & B200VIT_EPI_GELU) x = gelu_erf(x);
                 if (flags & B200VIT_EPI_RESIDUAL) x += p.resid[(size_t)row * p.ldo + cc];
-                if (out_f32) out_f32[(size_t)row * p.ldo + cc] = x;
+                if (p.out_f32) p.out_f32[(size_t)row * p.ldo + cc] = x;
                 const __nv_bfloat16 xb = __float2bfloat16_rn(x);
                 if (p.out_bf16) p.out_bf16[(size_t)row * p.ldo + cc] = xb;
                 if (flags & B200VIT_EPI_STATS) {
@@ -362,112 +342,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.num_m_tiles = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
   p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int tiles = p.num_m_tiles * p.num_n_tiles * (p.splits > 1 ? p.splits : 1);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, p);
   B200_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
-}
-
-
-// Second half of a split-K GEMM: out = epilogue(sum_s partial[s]) with exactly the epilogue arithmetic of the tensor
-// kernels above (same FMAs in the same order; the K sum itself is associated differently, so results differ from the
-// un-split kernel in the last bits -- deterministically: partials are added in index order).  One warp per row, lane l
-// owns columns 4 l .. 4 l + 3 of every 128-column group; group g is exactly statistics slot g (N > 128).
-__global__ void __launch_bounds__(256)
-splitk_epilogue_kernel(const float* __restrict__ part, long long split_stride, int splits, const GemmParams p) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= p.M) return;
-  const int flags = p.flags;
-  float mu = 0.f, rstd = 1.f;
-  if (flags & B200VIT_EPI_LNFOLD) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < p.ln_parts; ++i) {
-      const float2 ss = *reinterpret_cast<const float2*>(p.ln_sums + 2 * ((size_t)row * p.ln_parts + i));
-      s1 += ss.x;
-      s2 += ss.y;
-    }
-    mu = s1 * p.ln_inv_dim;
-    const float var = fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f);
-    rstd = rsqrtf(var + p.ln_eps);
-  }
-  const bool fold = (flags & B200VIT_EPI_LNFOLD) != 0;
-  for (int g = 0; g * 128 < p.N; ++g) {
-    const int col = g * 128 + 4 * lane;
-    float st_sum = 0.f, st_sq = 0.f;
-    if (col < p.N) {                       // N is a multiple of 4 (checked by the host)
-      float4 a = *reinterpret_cast<const float4*>(part + (size_t)row * p.ldo + col);
-      for (int s = 1; s < splits; ++s) {
-        const float4 b = *reinterpret_cast<const float4*>(part + (size_t)s * split_stride + (size_t)row * p.ldo + col);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      }
-      float v[4] = {a.x, a.y, a.z, a.w};
-      if (flags & (B200VIT_EPI_LNFOLD | B200VIT_EPI_BIAS)) {
-        float cv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (flags & B200VIT_EPI_BIAS) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-          cv[0] = b0.x; cv[1] = b0.y; cv[2] = b0.z; cv[3] = b0.w;
-        }
-        if (fold) {
-          const float4 s0 = *reinterpret_cast<const float4*>(p.col_s + col);
-          const float sv[4] = {s0.x, s0.y, s0.z, s0.w};
-          const float k = -rstd * mu;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cv[i] = fmaf(k, sv[i], cv[i]);
-        }
-        const float rs = fold ? rstd : 1.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = fmaf(v[i], rs, cv[i]);
-      }
-      if (flags & B200VIT_EPI_GELU) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
-      }
-      if (flags & B200VIT_EPI_RESIDUAL) {
-        const float4 r0 = *reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldo + col);
-        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      }
-      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
-      uint2 pk;
-      pk.x = pack_bf16x2(v[0], v[1]);
-      pk.y = pack_bf16x2(v[2], v[3]);
-      if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)row * p.ldo + col) = pk;
-      if (flags & B200VIT_EPI_STATS) {
-        const uint32_t w[2] = {pk.x, pk.y};
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float lo = __uint_as_float(w[i] << 16);
-          const float hi = __uint_as_float(w[i] & 0xFFFF0000u);
-          st_sum += lo + hi;
-          st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
-        }
-      }
-    }
-    if (flags & B200VIT_EPI_STATS) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
-        st_sq += __shfl_xor_sync(0xffffffffu, st_sq, o);
-      }
-      if (lane == 0) *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)row * p.stats_parts + g)) = make_float2(st_sum, st_sq);
-    }
-  }
-}
-
-// How many K splits a small-M GEMM gets: enough (m, n, split) tiles to give every SM one, at least two k blocks per
-// split, at most 16, and the fp32 partials [splits][M][ldo] must fit the caller's workspace.  1 = do not split.
-static int choose_splits(int M, int N, int K, long long ldo, long long workspace_bytes) {
-  if (M > 1024 || N <= 128 || (N & 3) || K < 512 || workspace_bytes <= 0) return 1;
-  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
-  if (tiles * 2 > num_sms()) return 1;
-  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
-  int splits = (num_sms() + tiles - 1) / tiles;
-  if (splits > kb / 2) splits = kb / 2;
-  if (splits > 16) splits = 16;
-  while (splits > 1 && (long long)splits * M * ldo * 4 > workspace_bytes) --splits;
-  return splits < 2 ? 1 : splits;
 }
 
 }  // namespace b200
@@ -481,15 +361,6 @@ extern "C" int b200vit_gemm_bf16(const void* A, int64_t lda, const void* W, int6
                                  float* out_f32, int64_t ldo, const float* bias, const float* resid,
                                  const float* ln_sums, int ln_parts, float ln_eps, const float* col_s,
                                  float* stats_out, int M, int N, int K, int flags, void* stream) {
-  return b200vit_gemm_bf16_ws(A, lda, W, ldw, out_bf16, out_f32, ldo, bias, resid, ln_sums, ln_parts, ln_eps, col_s,
-                              stats_out, M, N, K, flags, nullptr, 0, stream);
-}
-
-extern "C" int b200vit_gemm_bf16_ws(const void* A, int64_t lda, const void* W, int64_t ldw, void* out_bf16,
-                                    float* out_f32, int64_t ldo, const float* bias, const float* resid,
-                                    const float* ln_sums, int ln_parts, float ln_eps, const float* col_s,
-                                    float* stats_out, int M, int N, int K, int flags, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(A && W, "gemm: A/W must not be null");
   B200_CHECK_ARG(out_bf16 || out_f32, "gemm: need at least one output");
@@ -546,26 +417,6 @@ extern "C" int b200vit_gemm_bf16_ws(const void* A, int64_t lda, const void* W, i
     const uint32_t box[2] = {(uint32_t)BLOCK_K, block_n};
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
-  }
-  // small M with a workspace: split K over more CTAs, then one row kernel adds the partials and applies the epilogue
-  const int want = choose_splits(M, N, K, ldo, workspace ? workspace_bytes : 0);
-  if (want > 1 && wide && (ldo & 3) == 0 && al16(workspace)) {
-    const int kb = (K + BLOCK_K - 1) / BLOCK_K;
-    GemmParams q = p;
-    q.flags = 0;
-    q.out_bf16 = nullptr;
-    q.out_f32 = reinterpret_cast<float*>(workspace);
-    q.bias = q.resid = q.ln_sums = q.col_s = nullptr;
-    q.stats_out = nullptr;
-    q.kb_per_split = (kb + want - 1) / want;
-    q.splits = (kb + q.kb_per_split - 1) / q.kb_per_split;   // no empty split
-    q.split_stride = (long long)M * ldo;
-    int rc = launch_gemm<256, 4>(tmA, tmB, q, st);
-    if (rc) return rc;
-    splitk_epilogue_kernel<<<(M + 7) / 8, 256, 0, st>>>(q.out_f32, q.split_stride, q.splits, p);
-    B200_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-    return 0;
   }
   if (wide) return launch_gemm<256, 4>(tmA, tmB, p, st);
   return launch_gemm<128, 6>(tmA, tmB, p, st);

@@ -27,9 +27,6 @@ _FORCE_EAGER_ENV = "B200VIT_DISABLE_FUSED"
 _LN_MODE_ENV = "B200VIT_LN_MODE"      # "fold" (default) | "exact"
 _PATCH_MODE_ENV = "B200VIT_PATCH_MODE"  # "tma" (default: im2col-free 16x16 patch embedding) | "gather"
 _HOST_LOOP_ENV = "B200VIT_HOST_LOOP"    # "c" (default: all layers in one b200vit_encoder_blocks call) | "python"
-# "0" (default) | "1": batches of <= 1024 token rows split K of every encoder GEMM over more CTAs (lower latency at
-# batch 1..4; the K sum is then associated differently, so the bit-exact batch-SIZE invariance of the default is traded)
-_SPLITK_ENV = "B200VIT_SPLITK"
 
 
 def ln_mode() -> str:
@@ -276,7 +273,7 @@ class TransformerEngine:
         attn0, ff0 = next(iter(self._layers()))
         D, I, Hd = attn0.dim, attn0.heads * attn0.dim_head, ff0.hidden_dim
         # one workspace per (shape, stream): two streams running the same model must not share scratch buffers
-        key = (M, D, I, Hd, device, torch.cuda.current_stream(device).cuda_stream, os.environ.get(_SPLITK_ENV, "0"))
+        key = (M, D, I, Hd, device, torch.cuda.current_stream(device).cuda_stream)
         if self.ws_key != key:
             bf = dict(device=device, dtype=torch.bfloat16)
             self.ws = {
@@ -290,16 +287,8 @@ class TransformerEngine:
                 "stats_b": torch.empty(M, _lib.stats_parts(D), 2, device=device, dtype=torch.float32),
             }
             w = self.ws
-            # small batches (M <= 1024 rows): scratch for split-K partials, [splits <= 16][M][widest output] fp32,
-            # capped at 64 MB (the library takes fewer splits if it is short)
-            w["splitk"] = None
-            if M <= 1024 and os.environ.get(_SPLITK_ENV, "0") == "1":
-                w["splitk"] = torch.empty(min(64 << 20, 16 * M * max(3 * I, Hd, D) * 4), device=device,
-                                          dtype=torch.uint8)
-            sk = w["splitk"]
             self.c_ws = _lib.EncoderWs(w["xn"].data_ptr(), w["qkv"].data_ptr(), w["o"].data_ptr(), w["h"].data_ptr(),
-                                       w["stats_in"].data_ptr(), w["stats_a"].data_ptr(), w["stats_b"].data_ptr(),
-                                       None if sk is None else sk.data_ptr(), 0 if sk is None else sk.numel())
+                                       w["stats_in"].data_ptr(), w["stats_a"].data_ptr(), w["stats_b"].data_ptr())
             self.ws_key = key
         return self.ws
 
@@ -348,15 +337,14 @@ class TransformerEngine:
                                        ln_eps=attn.norm.eps, head_gamma=t[f"{i}.gqk"], norm_heads=2 * attn.heads)
                 else:
                     _lib.gemm(xb, t[f"{i}.qkv.wg"], out_bf16=ws["qkv"], bias=t[f"{i}.qkv.t"],
-                              ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"], ln_eps=attn.norm.eps,
-                              workspace=ws["splitk"])
+                              ln_sums=ws["stats_in"] if i == 0 else sa, col_s=t[f"{i}.qkv.s"], ln_eps=attn.norm.eps)
                 self._attention(ws, B, N, attn)
                 _lib.gemm(ws["o"], t[f"{i}.out.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.out.b"], resid=x,
-                          stats_out=sb, workspace=ws["splitk"])
+                          stats_out=sb)
                 _lib.gemm(xb, t[f"{i}.fc1.wg"], out_bf16=ws["h"], bias=t[f"{i}.fc1.t"], gelu=True, ln_sums=sb,
-                          col_s=t[f"{i}.fc1.s"], ln_eps=ff.parts()[0].eps, workspace=ws["splitk"])
+                          col_s=t[f"{i}.fc1.s"], ln_eps=ff.parts()[0].eps)
                 _lib.gemm(ws["h"], t[f"{i}.fc2.w"], out_f32=x, out_bf16=xb, bias=t[f"{i}.fc2.b"], resid=x,
-                          stats_out=sa, workspace=ws["splitk"])
+                          stats_out=sa)
             return
         for i, (attn, ff) in enumerate(self._layers()):
             _lib.layernorm(x, t[f"{i}.ln1.w"], t[f"{i}.ln1.b"], out_bf16=ws["xn"], eps=attn.norm.eps)
