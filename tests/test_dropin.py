@@ -234,3 +234,20 @@ def test_recorder_and_extractor_twins():
         with torch.no_grad():
             _, ref_attns = RefRecorder(r)(img)
         assert torch.allclose(ref_attns, attns, atol=1e-6)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference checkout not present")
+def test_reference_accept_video_wrapper_runs_on_the_dropin():
+    """AcceptVideoWrapper (reference accept_video_wrapper.py:26-150) reads `image_net.patch_size` and feeds the frames
+    of a clip through `image_net.forward` as one batch: same output as on the reference's own ViT."""
+    import importlib
+    ours, ref = _pair_with_reference(image_size=32, patch_size=8, num_classes=7, dim=32, depth=1, heads=2, mlp_dim=48,
+                                     dim_head=16)
+    Wrapper = importlib.import_module("vit_pytorch.accept_video_wrapper").AcceptVideoWrapper
+    a = Wrapper(ours, add_time_pos_emb=True, time_seq_len=4, dim_emb=7)
+    b = Wrapper(ref, add_time_pos_emb=True, time_seq_len=4, dim_emb=7)
+    b.load_state_dict(a.state_dict())
+    assert a.patch_size == b.patch_size == (8, 8)
+    video = torch.randn(2, 3, 4, 32, 32)
+    with torch.no_grad():
+        assert torch.allclose(a(video), b(video), rtol=1e-5, atol=1e-6)
