@@ -353,3 +353,28 @@ def test_trained_like_statistics_stay_below_the_bf16_floor(mode, monkeypatch):
           f"fused max {d.max():.4f} mean {d.mean():.5f}; bf16 graph max {f.max():.4f} mean {f.mean():.5f}")
     assert torch.isfinite(out).all()
     assert d.mean() <= f.mean() * 1.05 + 1e-4 and d.max() <= f.max() * 1.5 + 1e-3
+
+
+def test_reference_distill_wrapper_runs_its_teacher_on_the_fused_path():
+    """DistillWrapper (reference distill.py:104-152) calls `teacher(img)` under no_grad: with the drop-in as the
+    teacher (cuda, bf16) that call is the fused sm_100a forward; the student is the reference's own DistillableViT."""
+    from conftest import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("no reference package (neither /root/reference nor baseline/_ref)")
+    import importlib
+    import_reference()
+    distill = importlib.import_module("vit_pytorch.distill")
+    kw = dict(image_size=64, patch_size=8, num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256)
+    torch.manual_seed(0)
+    teacher = ViT(**kw).eval().to(DEV, torch.bfloat16)
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    student = distill.DistillableViT(**kw).to(DEV, torch.bfloat16)
+    wrapper = distill.DistillWrapper(student=student, teacher=teacher, temperature=3, alpha=0.5).to(DEV, torch.bfloat16)
+    img = torch.randn(4, 3, 64, 64, device=DEV).bfloat16()
+    labels = torch.randint(0, 10, (4,), device=DEV)
+    _lib.reset_launch_count()
+    loss = wrapper(img, labels)
+    assert _lib.launch_count() >= 3 + 5 * 2                      # the teacher forward ran in the library's kernels
+    loss.backward()                                              # and the student still trains through the wrapper
+    assert torch.isfinite(loss) and student.mlp_head.weight.grad is not None
